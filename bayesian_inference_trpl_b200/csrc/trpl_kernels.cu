@@ -1,0 +1,1133 @@
+// trpl_kernels.cu -- sm_100a kernels + C ABI of libtrpl_b200.so (see include/trpl_b200.h).
+//
+// Hot path replaced: pvSimPCR.py:14-401 (tEvol/iterate/pcreduce/norm2 + pvSim host driver) and
+// probs.py:20-85 (kernel_lnP, log_kernel), plus the glue bayeslib.simulate runs between them
+// (bayeslib.py:150-196).  Written from scratch for B200; nothing here is a translation of the
+// numba kernels:
+//
+//   * one WARP owns one (sample, curve) simulation for its whole time integration; lane p holds
+//     M consecutive grid nodes (L = 128 -> M = 4) of N, P, E and the BDF history sums in
+//     REGISTERS; the four older BDF levels live in a lane-private shared-memory ring (no
+//     barriers anywhere -- the reference round-trips the state through global memory every
+//     step and needs ~50 __syncthreads per Newton iteration);
+//   * each tridiagonal system is solved by a register-local partition sweep (M-1 interior rows
+//     per lane eliminated in place) + a 32-lane parallel cyclic reduction on the interface
+//     unknowns done with warp shuffles (5 normalised stages instead of the reference's
+//     log2(L)-1 shared-memory stages over all L rows);
+//   * the L1 residual norms of both species are reduced together with a 4-value butterfly;
+//   * PL(t) is a warp reduction; 32 consecutive PL values are staged one per lane and then
+//     consumed together: written with one coalesced store (trpl_solve_pl) and/or turned into
+//     log10, time-interpolated onto the observation times and accumulated into the squared
+//     log-residual sum (trpl_solve_loglik) -- PL never goes to HBM on the fused path;
+//   * warps fetch work items from a global atomic counter (persistent CTAs), so a slowly
+//     converging sample never idles a wave.
+//
+// All arithmetic is FP64 like the reference (pvSimPCR.py:11,113-125).  Divisions are replaced by
+// a Newton-refined reciprocal (MUFU.RCP64H seed), accurate to <= 1 ulp; see DESIGN.md.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+#include <limits.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "trpl_b200.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS_PER_CTA = 4;
+
+struct ObsDev {
+    int n;
+    int pad_;
+    const int *hi;
+    const double *whi;
+    const double *wlo;
+    const double *val;
+};
+
+struct CurveDev {
+    double scales[TRPL_NPAR];
+    double init_mul;      // dx^3, or 1 when the profile is already in grid units
+    double redim;         // dx^2 * dt                         (pvSimPCR.py:393)
+    const double *init;   // [L]
+    void *pl_out;         // row base for sample 0, or nullptr
+    int t_last;           // last time index to integrate to (<= T)
+    int pad_;
+    ObsDev obs[TRPL_MAX_EXP];
+};
+
+struct KArgs {
+    const double *x;
+    long long ldx;
+    long long S;
+    long long pl_stride;
+    double TOL;
+    double *sse;                 // [E][C][S] or nullptr
+    int *status;                 // [C][S] or nullptr
+    long long *iters;            // [C][S] or nullptr
+    unsigned long long *counter; // work-item counter (zeroed by the host)
+    int mag_col;                 // < 0: no magnitude offset
+    int C, E, L, plT, max_iter, max_order, flags, pl_dtype;
+    CurveDev curves[TRPL_MAX_CURVES];
+};
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp64(double x)
+{
+    // MUFU.RCP64H seed + cubic step + one Newton step (no slow path: operands here are
+    // normal, finite and far from the exponent limits).
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
+
+// Tridiagonal solve, M rows per lane (row n = M*lane + j):  l[j] x[n-1] + d[j] x[n] + u[j] x[n+1] = b[j].
+// Rows outside the physical system must be identity rows (l=u=0, d=1).  l of the first row
+// and u of the last physical row must be 0.
+template <int M>
+__device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double (&d)[M],
+                                              const double (&u)[M], const double (&b)[M],
+                                              double (&x)[M])
+{
+    double Lr, Dr, Ur, Br;
+    double c[M > 1 ? M - 1 : 1], y[M > 1 ? M - 1 : 1], v[M > 1 ? M - 1 : 1], w[M > 1 ? M - 1 : 1];
+    if constexpr (M > 1) {
+        // interior rows 0..M-2:  x_j = y_j - v_j * s_left - w_j * s_own
+        double inv = rcp64(d[0]);
+        c[0] = u[0] * inv;
+        y[0] = b[0] * inv;
+        v[0] = l[0] * inv;
+#pragma unroll
+        for (int j = 1; j < M - 1; j++) {
+            double den = fma(-l[j], c[j - 1], d[j]);
+            inv = rcp64(den);
+            c[j] = u[j] * inv;
+            y[j] = fma(-l[j], y[j - 1], b[j]) * inv;
+            v[j] = (-l[j] * v[j - 1]) * inv;
+        }
+        w[M - 2] = c[M - 2];
+#pragma unroll
+        for (int j = M - 3; j >= 0; j--) {
+            y[j] = fma(-c[j], y[j + 1], y[j]);
+            v[j] = fma(-c[j], v[j + 1], v[j]);
+            w[j] = -c[j] * w[j + 1];
+        }
+        // interface row (local M-1) couples s_left, s_own and the next lane's first interior row
+        const double y0n = __shfl_down_sync(FULL, y[0], 1);
+        const double v0n = __shfl_down_sync(FULL, v[0], 1);
+        const double w0n = __shfl_down_sync(FULL, w[0], 1);
+        const double lr = l[M - 1], ur = u[M - 1];
+        Lr = -lr * v[M - 2];
+        Dr = fma(-ur, v0n, fma(-lr, w[M - 2], d[M - 1]));
+        Ur = -ur * w0n;
+        Br = fma(-ur, y0n, fma(-lr, y[M - 2], b[M - 1]));
+    } else {
+        Lr = l[0]; Dr = d[0]; Ur = u[0]; Br = b[0];
+    }
+    // 32-lane parallel cyclic reduction with unit diagonal
+    {
+        double inv = rcp64(Dr);
+        Lr *= inv; Ur *= inv; Br *= inv;
+    }
+#pragma unroll
+    for (int rf = 1; rf < 32; rf <<= 1) {
+        const double Lm = __shfl_up_sync(FULL, Lr, rf);
+        const double Um = __shfl_up_sync(FULL, Ur, rf);
+        const double Bm = __shfl_up_sync(FULL, Br, rf);
+        const double Lp = __shfl_down_sync(FULL, Lr, rf);
+        const double Up = __shfl_down_sync(FULL, Ur, rf);
+        const double Bp = __shfl_down_sync(FULL, Br, rf);
+        const double D = fma(-Lp, Ur, fma(-Um, Lr, 1.0));
+        const double B = fma(-Bp, Ur, fma(-Bm, Lr, Br));
+        const double Ln = -Lm * Lr;
+        const double Un = -Up * Ur;
+        const double inv = rcp64(D);
+        Br = B * inv;
+        Lr = Ln * inv;
+        Ur = Un * inv;
+    }
+    x[M - 1] = Br;
+    if constexpr (M > 1) {
+        const double sl = __shfl_up_sync(FULL, Br, 1);
+#pragma unroll
+        for (int j = 0; j < M - 1; j++) x[j] = fma(-w[j], Br, fma(-v[j], sl, y[j]));
+    }
+}
+
+// lane-private ring of the 4 older BDF levels: [slot 0..3][field N,P,E][M doubles per lane]
+template <int M>
+struct Ring {
+    double *base;   // warp base + lane offset
+    // element (slot, field, j): chunks of 2 doubles per lane keep 16-byte accesses conflict-free
+    __device__ __forceinline__ void load(int slot, int field, double (&h)[M]) const
+    {
+        if constexpr (M == 1) {
+            h[0] = base[(slot * 3 + field) * 32];
+        } else {
+#pragma unroll
+            for (int q = 0; q < M / 2; q++) {
+                const double2 t = *reinterpret_cast<const double2 *>(
+                    base + ((slot * 3 + field) * (M / 2) + q) * 64);
+                h[2 * q] = t.x;
+                h[2 * q + 1] = t.y;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(int slot, int field, const double (&h)[M]) const
+    {
+        if constexpr (M == 1) {
+            base[(slot * 3 + field) * 32] = h[0];
+        } else {
+#pragma unroll
+            for (int q = 0; q < M / 2; q++)
+                *reinterpret_cast<double2 *>(base + ((slot * 3 + field) * (M / 2) + q) * 64) =
+                    make_double2(h[2 * q], h[2 * q + 1]);
+        }
+    }
+};
+
+struct WarpScratch {      // per-warp shared scratch touched once every 32 PL samples
+    double sse[TRPL_MAX_EXP];
+    int pos[TRPL_MAX_EXP];
+};
+
+// ---------------------------------------------------------------------------------------------
+// one (sample, curve) simulation, executed by one warp
+// ---------------------------------------------------------------------------------------------
+template <int M, bool PAD>
+__device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long long s,
+                                        double *ring_warp, WarpScratch *ws, const int lane)
+{
+    const CurveDev &cv = a.curves[c];
+    const int L = a.L;
+    const int flags = a.flags;
+    const bool emu32 = (flags & TRPL_F_EMULATE_F32) != 0;
+
+    // ---- parameters: non-dimensionalise (pvSimPCR.py:327-331), one column per lane, then broadcast
+    double mpl = 0.0;
+    if (lane < TRPL_NPAR) mpl = a.x[s * a.ldx + lane] * cv.scales[lane];
+    const double N0 = __shfl_sync(FULL, mpl, 0), P0 = __shfl_sync(FULL, mpl, 1);
+    const double DN = __shfl_sync(FULL, mpl, 2), DP = __shfl_sync(FULL, mpl, 3);
+    const double rate = __shfl_sync(FULL, mpl, 4);
+    const double sr0 = __shfl_sync(FULL, mpl, 5), srL = __shfl_sync(FULL, mpl, 6);
+    const double CN = __shfl_sync(FULL, mpl, 7), CP = __shfl_sync(FULL, mpl, 8);
+    const double tauN = __shfl_sync(FULL, mpl, 9), tauP = __shfl_sync(FULL, mpl, 10);
+    const double Lam = __shfl_sync(FULL, mpl, 11);
+    const double N0P0 = N0 * P0;
+    const double hDN = 0.5 * DN, hDP = 0.5 * DP, hLam = 0.5 * Lam;
+    const double TOL = a.TOL;
+    const double mag = (a.mag_col >= 0) ? a.x[s * a.ldx + a.mag_col] : 0.0;
+
+    // ---- geometry of this lane
+    const int last_lane = (L - 1) / M;         // lane owning node L-1 (at j = M-1 since L % M == 0)
+    bool ev[M + 1];                            // edge m = M*lane + j is an interior edge (1..L-1)
+#pragma unroll
+    for (int j = 0; j <= M; j++) {
+        const int m = M * lane + j;
+        ev[j] = (m >= 1) && (m <= L - 1);
+    }
+    bool nv[M];                                // node n = M*lane + j exists
+#pragma unroll
+    for (int j = 0; j < M; j++) nv[j] = PAD ? (M * lane + j < L) : true;
+    // surface rows: lane 0 applies the front surface to j=0, last_lane the back surface to j=M-1
+    const bool is_first = (lane == 0), is_last = (lane == last_lane);
+    const double srf = is_first ? sr0 : (is_last ? srL : 0.0);
+
+    // ---- initial state (pvSimPCR.py:339-362): N = N0 + dN, P = P0 + dN, E = 0
+    double N[M], P[M], E[M];
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+        const int n = M * lane + j;
+        double dn = 0.0;
+        if (n < L) dn = cv.init[n] * cv.init_mul;
+        N[j] = nv[j] ? N0 + dn : 0.0;
+        P[j] = nv[j] ? P0 + dn : 0.0;
+        E[j] = 0.0;
+    }
+    Ring<M> ring;
+    ring.base = ring_warp + ((M == 1) ? lane : 2 * lane);
+    {
+        double z[M];
+#pragma unroll
+        for (int j = 0; j < M; j++) z[j] = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < 4; sl++)
+#pragma unroll
+            for (int f = 0; f < 3; f++) ring.store(sl, f, z);
+    }
+    if (lane < TRPL_MAX_EXP) {
+        ws->sse[lane] = 0.0;
+        ws->pos[lane] = 0;
+    }
+    __syncwarp();
+
+    // neighbour values carried across iterations and steps
+    double Nl = __shfl_up_sync(FULL, N[M - 1], 1), Nr = __shfl_down_sync(FULL, N[0], 1);
+    double Pl = __shfl_up_sync(FULL, P[M - 1], 1), Pr = __shfl_down_sync(FULL, P[0], 1);
+    double En = 0.0;   // E on edge M*lane + M (owned by the next lane)
+
+    const double mLN0P0 = -(double)L * N0P0;   // pvSimPCR.py:278
+    const int t_last = cv.t_last;
+    const int plT = a.plT;
+    const int n_pl = t_last / plT + 1;
+    double keep = 0.0;          // PL sample staged in this lane
+    double lp_carry = 0.0;      // log PL of the sample preceding the current block of 32
+    double pl0 = 1.0;           // PL(t=0) for self-normalisation
+    long long iters_total = 0;
+    int status = 0;
+    int pl_idx = 0;             // index of the next PL sample
+    int t_next_pl = 0;
+
+    // consume a block of `cnt` staged PL samples starting at index idx0
+    auto flush = [&](const int idx0, const int cnt) {
+        double val;
+        if (emu32) {
+            float f = (float)keep;             // value rounded on store into the f32 buffer
+            f = f / (float)cv.redim;           // plI_main /= dx**2*dt in float32
+            val = (double)f;
+        } else {
+            val = keep / cv.redim;
+        }
+        if (cv.pl_out != nullptr && lane < cnt) {
+            if (a.pl_dtype == TRPL_F32)
+                reinterpret_cast<float *>(cv.pl_out)[s * a.pl_stride + idx0 + lane] = (float)val;
+            else
+                reinterpret_cast<double *>(cv.pl_out)[s * a.pl_stride + idx0 + lane] = val;
+        }
+        if (a.E == 0) return;
+        if (flags & TRPL_F_SELF_NORMALIZE) {
+            if (idx0 == 0) pl0 = __shfl_sync(FULL, val, 0);
+            val = emu32 ? (double)((float)val / (float)pl0) : val / pl0;
+        }
+        double lp = val;
+        if (flags & TRPL_F_LOG_PL) {
+            if (emu32) {
+                float f = (float)val;
+                if ((double)f < DBL_MIN) f = 0.0f;   // (float)sys.float_info.min == 0  (probs.py:72-73)
+                lp = (double)log10f(f);
+            } else {
+                lp = log10(val < DBL_MIN ? DBL_MIN : val);
+            }
+        }
+        for (int e = 0; e < a.E; e++) {
+            const ObsDev &ob = cv.obs[e];
+            int pos = ws->pos[e];
+            double acc = 0.0;
+            for (;;) {
+                const int i = pos + lane;
+                const int h = (i < ob.n) ? ob.hi[i] : INT_MAX;
+                const bool mine = h < idx0 + cnt;
+                const unsigned bm = __ballot_sync(FULL, mine);
+                if (bm == 0u) break;
+                const int shi = mine ? h - idx0 : 0;       // 0..cnt-1
+                const int slo = shi - 1;                   // -1..cnt-2
+                const double y_hi = __shfl_sync(FULL, lp, shi & 31);
+                double y_lo = __shfl_sync(FULL, lp, slo & 31);
+                if (slo < 0) y_lo = lp_carry;
+                double sq = 0.0;
+                if (mine) {
+                    // scipy interp1d._call_linear: w_hi*y_hi + w_lo*y_lo, no contraction
+                    const double yi = __dadd_rn(__dmul_rn(ob.whi[i], y_hi), __dmul_rn(ob.wlo[i], y_lo));
+                    double err = yi + mag;                  // probs.py:33-38
+                    err -= ob.val[i];
+                    sq = err * err;
+                }
+                acc += warp_sum(sq);
+                const int took = __popc(bm);
+                pos += took;
+                if (took < 32) break;
+            }
+            if (lane == 0) {
+                ws->pos[e] = pos;
+                ws->sse[e] += acc;
+            }
+        }
+        lp_carry = __shfl_sync(FULL, lp, cnt - 1);
+        __syncwarp();
+    };
+
+    // =========================================================================================
+    // time loop (pvSimPCR.py:237-293): t = 0 .. t_last, PL(t) emitted from the state at time t
+    // =========================================================================================
+    bool failed = false;
+    int t;
+    for (t = 0; t <= t_last; t++) {
+        // ---- PL(t) = rate * (sum_n N*P - L*N0*P0)                          (pvSimPCR.py:276-281)
+        bool emitted = false;
+        if (t == t_next_pl) {
+            emitted = true;
+            double part = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; j++) part = fma(N[j], P[j], part);
+            const double tot = warp_sum(part);
+            const double plraw = rate * (tot + mLN0P0);
+            if (lane == (pl_idx & 31)) keep = plraw;
+            t_next_pl += plT;
+            pl_idx++;
+        }
+
+        // ---- BDF coefficients, order ramp 1..5                            (pvSimPCR.py:241-250)
+        double a0, a1, a2, a3, a4, a5;
+        {
+            int order = t + 1;
+            if (order > 5) order = 5;
+            if (order > a.max_order) order = a.max_order;
+            a2 = a3 = a4 = a5 = 0.0;
+            if (order == 1) { a0 = 1.0; a1 = -1.0; }
+            else if (order == 2) { a0 = 1.5; a1 = -2.0; a2 = 0.5; }
+            else if (order == 3) { a0 = 11.0 / 6; a1 = -3.0; a2 = 1.5; a3 = -1.0 / 3; }
+            else if (order == 4) { a0 = 25.0 / 12; a1 = -4.0; a2 = 3.0; a3 = -4.0 / 3; a4 = 0.25; }
+            else { a0 = 137.0 / 60; a1 = -5.0; a2 = 5.0; a3 = -10.0 / 3; a4 = 1.25; a5 = -0.2; }
+        }
+
+        // ---- history sums bU = a1 U(t) + a2 U(t-1) + ... + a5 U(t-4)       (pvSimPCR.py:133-135)
+        double bN[M], bP[M], bE[M];
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            bN[j] = a1 * N[j];
+            bP[j] = a1 * P[j];
+            bE[j] = a1 * E[j];
+        }
+        {
+            const double ac[4] = {a2, a3, a4, a5};
+#pragma unroll
+            for (int i = 1; i <= 4; i++) {
+                const int slot = (t - i) & 3;
+                double h[M];
+                ring.load(slot, 0, h);
+#pragma unroll
+                for (int j = 0; j < M; j++) bN[j] = fma(ac[i - 1], h[j], bN[j]);
+                ring.load(slot, 1, h);
+#pragma unroll
+                for (int j = 0; j < M; j++) bP[j] = fma(ac[i - 1], h[j], bP[j]);
+                ring.load(slot, 2, h);
+#pragma unroll
+                for (int j = 0; j < M; j++) bE[j] = fma(ac[i - 1], h[j], bE[j]);
+            }
+            const int slot = t & 3;    // level t replaces level t-4
+            ring.store(slot, 0, N);
+            ring.store(slot, 1, P);
+            ring.store(slot, 2, E);
+        }
+
+        // ---- Newton / Gauss-Seidel iteration                              (pvSimPCR.py:147-216)
+        int it = 0;
+        bool nonfinite = false;
+        for (;;) {
+            double l[M], d[M], u[M], b[M];
+            double rN = 0.0, sbN = 0.0, rP = 0.0, sbP = 0.0;
+
+            // ======== N system (P, E frozen) ========
+            {
+                double cu[M + 1], cl[M + 1];   // edge coefficients: cu[m] = upper of row m-1, cl[m] = lower of row m
+#pragma unroll
+                for (int j = 0; j <= M; j++) {
+                    const double Ej = (j < M) ? E[j] : En;
+                    cu[j] = sel(ev[j], fma(-hDN, Ej, -DN), 0.0);     // DN*(-E/2 - 1)
+                    cl[j] = sel(ev[j], fma(hDN, Ej, -DN), 0.0);      // DN*(+E/2 - 1)
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const double Nj = N[j], Pj = P[j];
+                    const double tp = fma(Nj, tauP, Pj * tauN);
+                    const double NP = Nj * Pj;
+                    const double npp = NP - N0P0;
+                    const double r = rcp64(tp);
+                    const double q = fma(-tauP, npp, Pj * tp);
+                    const double srh = (q * r) * r;
+                    const double aug = fma(CP, Pj * Pj, CN * (NP + npp));
+                    const double nds = fma(rate, Pj, srh) + aug;             // = -ds
+                    l[j] = cl[j];
+                    u[j] = cu[j + 1];
+                    d[j] = ((a0 - cu[j]) - cl[j + 1]) + nds;
+                    const double g = fma(CN, Nj, fma(CP, Pj, rate + r));
+                    b[j] = fma(nds, Nj, -fma(g, npp, bN[j]));
+                }
+                // surface recombination rows                                 (pvSimPCR.py:164-170)
+                {
+                    const double Ns = is_first ? N[0] : N[M - 1];
+                    const double Ps = is_first ? P[0] : P[M - 1];
+                    const double rs = rcp64(Ns + Ps);
+                    const double nd = (srf * fma(Ps, Ps, N0P0)) * (rs * rs);        // = -ds0
+                    const double db = fma(-nd, Ns, (srf * fma(Ns, Ps, -N0P0)) * rs);
+                    d[0] += is_first ? nd : 0.0;
+                    b[0] -= is_first ? db : 0.0;
+                    d[M - 1] += is_last ? nd : 0.0;
+                    b[M - 1] -= is_last ? db : 0.0;
+                }
+                if (PAD) {
+#pragma unroll
+                    for (int j = 0; j < M; j++) {
+                        l[j] = sel(nv[j], l[j], 0.0);
+                        u[j] = sel(nv[j], u[j], 0.0);
+                        d[j] = sel(nv[j], d[j], 1.0);
+                        b[j] = sel(nv[j], b[j], 0.0);
+                    }
+                }
+                // L1 residual of the current iterate                         (pvSimPCR.py:172, :14-40)
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const double cm = (j == 0) ? Nl : N[j - 1];
+                    const double cp = (j == M - 1) ? Nr : N[j + 1];
+                    const double res = fma(l[j], cm, fma(d[j], N[j], fma(u[j], cp, -b[j])));
+                    rN += fabs(res);
+                    sbN += fabs(b[j]);
+                }
+                tridiag_solve<M>(l, d, u, b, N);
+                Nl = __shfl_up_sync(FULL, N[M - 1], 1);
+                Nr = __shfl_down_sync(FULL, N[0], 1);
+            }
+
+            // ======== P system (new N) ========
+            {
+                double cu[M + 1], cl[M + 1];
+#pragma unroll
+                for (int j = 0; j <= M; j++) {
+                    const double Ej = (j < M) ? E[j] : En;
+                    cu[j] = sel(ev[j], fma(hDP, Ej, -DP), 0.0);      // DP*(+E/2 - 1)
+                    cl[j] = sel(ev[j], fma(-hDP, Ej, -DP), 0.0);     // DP*(-E/2 - 1)
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const double Nj = N[j], Pj = P[j];
+                    const double tp = fma(Nj, tauP, Pj * tauN);
+                    const double NP = Nj * Pj;
+                    const double npp = NP - N0P0;
+                    const double r = rcp64(tp);
+                    const double q = fma(-tauN, npp, Nj * tp);
+                    const double srh = (q * r) * r;
+                    const double aug = fma(CN, Nj * Nj, CP * (NP + npp));
+                    const double nds = fma(rate, Nj, srh) + aug;
+                    l[j] = cl[j];
+                    u[j] = cu[j + 1];
+                    d[j] = ((a0 - cu[j]) - cl[j + 1]) + nds;
+                    const double g = fma(CN, Nj, fma(CP, Pj, rate + r));
+                    b[j] = fma(nds, Pj, -fma(g, npp, bP[j]));
+                }
+                {
+                    const double Ns = is_first ? N[0] : N[M - 1];
+                    const double Ps = is_first ? P[0] : P[M - 1];
+                    const double rs = rcp64(Ns + Ps);
+                    const double nd = (srf * fma(Ns, Ns, N0P0)) * (rs * rs);
+                    const double db = fma(-nd, Ps, (srf * fma(Ns, Ps, -N0P0)) * rs);
+                    d[0] += is_first ? nd : 0.0;
+                    b[0] -= is_first ? db : 0.0;
+                    d[M - 1] += is_last ? nd : 0.0;
+                    b[M - 1] -= is_last ? db : 0.0;
+                }
+                if (PAD) {
+#pragma unroll
+                    for (int j = 0; j < M; j++) {
+                        l[j] = sel(nv[j], l[j], 0.0);
+                        u[j] = sel(nv[j], u[j], 0.0);
+                        d[j] = sel(nv[j], d[j], 1.0);
+                        b[j] = sel(nv[j], b[j], 0.0);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const double cm = (j == 0) ? Pl : P[j - 1];
+                    const double cp = (j == M - 1) ? Pr : P[j + 1];
+                    const double res = fma(l[j], cm, fma(d[j], P[j], fma(u[j], cp, -b[j])));
+                    rP += fabs(res);
+                    sbP += fabs(b[j]);
+                }
+                tridiag_solve<M>(l, d, u, b, P);
+                Pl = __shfl_up_sync(FULL, P[M - 1], 1);
+                Pr = __shfl_down_sync(FULL, P[0], 1);
+            }
+
+            // ======== E update on interior edges                           (pvSimPCR.py:205-209)
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                const double Nm = (j == 0) ? Nl : N[j - 1];
+                const double Pm = (j == 0) ? Pl : P[j - 1];
+                const double den = fma(hLam, fma(DP, P[j] + Pm, DN * (N[j] + Nm)), a0);
+                const double num = fma(Lam, fma(DP, P[j] - Pm, -(DN * (N[j] - Nm))), -bE[j]);
+                E[j] = sel(ev[j], num * rcp64(den), 0.0);
+            }
+            En = __shfl_down_sync(FULL, E[0], 1);
+
+            // ======== convergence test on the residuals of the previous iterate (pvSimPCR.py:213-216)
+            it++;
+            {
+                const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+                double k0 = hi16 ? sbN : rN, k1 = hi16 ? sbP : rP;
+                const double s0 = hi16 ? rN : sbN, s1 = hi16 ? rP : sbP;
+                k0 += __shfl_xor_sync(FULL, s0, 16);
+                k1 += __shfl_xor_sync(FULL, s1, 16);
+                double k = hi8 ? k1 : k0;
+                const double sd = hi8 ? k0 : k1;
+                k += __shfl_xor_sync(FULL, sd, 8);
+                k += __shfl_xor_sync(FULL, k, 4);
+                k += __shfl_xor_sync(FULL, k, 2);
+                k += __shfl_xor_sync(FULL, k, 1);
+                const double other = __shfl_xor_sync(FULL, k, 16);
+                const double err = k / other;                 // lanes 0-7: errN, lanes 8-15: errP
+                const unsigned okm = __ballot_sync(FULL, err < TOL) & 0xffffu;
+                const unsigned nfm = __ballot_sync(FULL, !(fabs(err) <= DBL_MAX)) & 0xffffu;
+                if (nfm) { nonfinite = true; break; }
+                if (okm == 0xffffu) break;
+            }
+            if (it >= a.max_iter) break;
+        }
+        iters_total += it;
+        if (nonfinite || it >= a.max_iter) {                 // pvSimPCR.py:269-274
+            status |= nonfinite ? TRPL_ST_NONFINITE : TRPL_ST_NOCONV;
+            failed = true;
+            // the reference stops before emitting PL(t): un-count the sample staged for this step
+            if (emitted) pl_idx--;
+            break;
+        }
+        if (emitted && (pl_idx & 31) == 0) flush(pl_idx - 32, 32);
+    }
+
+    // ---- tail: partially filled block; after a failure everything from pl_idx on is NaN
+    if (pl_idx & 31) flush(pl_idx & ~31, pl_idx & 31);
+    if (failed && cv.pl_out != nullptr) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int i = pl_idx + lane; i < n_pl; i += 32) {
+            if (a.pl_dtype == TRPL_F32)
+                reinterpret_cast<float *>(cv.pl_out)[s * a.pl_stride + i] = (float)qnan;
+            else
+                reinterpret_cast<double *>(cv.pl_out)[s * a.pl_stride + i] = qnan;
+        }
+    }
+
+    // ---- results
+    __syncwarp();
+    if (lane == 0) {
+        const long long cs = (long long)c * a.S + s;
+        if (a.status) a.status[cs] = status;
+        if (a.iters) a.iters[cs] = iters_total;
+    }
+    if (a.sse != nullptr && lane < a.E) {
+        double v = ws->sse[lane];
+        if (failed && ws->pos[lane] < cv.obs[lane].n) v = __longlong_as_double(0x7ff8000000000000LL);
+        a.sse[((long long)lane * a.C + c) * a.S + s] = v;
+    }
+    __syncwarp();
+}
+
+template <int M, bool PAD>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+trpl_sim_kernel(const __grid_constant__ KArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ WarpScratch scratch[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32);
+    const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.counter, 1ULL);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= total) break;
+        const long long s = (long long)(item / (unsigned)a.C);
+        const int c = (int)(item % (unsigned)a.C);
+        run_sim<M, PAD>(a, c, s, ring_warp, &scratch[warp], lane);
+    }
+}
+
+// lnl[e][s] -= sum_c sse[e][c][s] (curves in order), status[s] = OR_c status[c][s]
+__global__ void trpl_finish_kernel(const double *sse, double *lnl, const int *status_cs,
+                                   int *status_s, long long S, int C, int E)
+{
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    for (int e = 0; e < E; e++) {
+        double p = lnl[e * S + s];
+        for (int c = 0; c < C; c++) p -= sse[((long long)e * C + c) * S + s];
+        lnl[e * S + s] = p;
+    }
+    if (status_s) {
+        int st = 0;
+        for (int c = 0; c < C; c++) st |= status_cs[(long long)c * S + s];
+        status_s[s] = st;
+    }
+}
+
+// ---- probs.fastlog / log_kernel (probs.py:64-85) ---------------------------------------------
+__global__ void trpl_log10_kernel_f64(double *x, long long n, double mn)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v = x[i];
+        if (v < mn) v = mn;
+        x[i] = log10(v);
+    }
+}
+__global__ void trpl_log10_kernel_f32(float *x, long long n, double mn)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v = x[i];
+        if ((double)v < mn) v = (float)mn;
+        x[i] = log10f(v);
+    }
+}
+
+// ---- probs.prob / kernel_lnP (probs.py:20-62): one warp per sample, coalesced row reads -------
+__global__ void trpl_lnp_kernel(double *P, const double *pl, long long S, long long n, long long ld,
+                                const double *values, const double *mag)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long j = warp; j < S; j += nwarps) {
+        const double m = mag[j];
+        const double *row = pl + j * ld;
+        double acc = 0.0;
+        for (long long i = lane; i < n; i += 32) {
+            double err = row[i] + m;
+            err -= values[i];
+            acc = fma(err, err, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) P[j] += (0.0 - acc);
+    }
+}
+
+// ---- shard-local log-sum-exp pieces (Visualization/utils.py:157-166) --------------------------
+__global__ void trpl_lse_max_kernel(const double *x, long long n, double *out)
+{
+    __shared__ double sh[32];
+    double m = -INFINITY;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = x[i];
+        if (v == v && v > m) m = v;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+        if (threadIdx.x == 0) {
+            // atomic max on doubles via ordered-integer trick
+            unsigned long long *addr = reinterpret_cast<unsigned long long *>(out);
+            unsigned long long old = *addr, assumed;
+            do {
+                assumed = old;
+                if (__longlong_as_double((long long)assumed) >= m) break;
+                old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(m));
+            } while (assumed != old);
+        }
+    }
+}
+__global__ void trpl_lse_sum_kernel(const double *x, long long n, double *out)
+{
+    __shared__ double sh[32];
+    const double mx = out[0];
+    double acc = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = x[i];
+        if (v == v) acc += exp(v - mx);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        acc = warp_sum(acc);
+        if (threadIdx.x == 0) atomicAdd(out + 1, acc);
+    }
+}
+__global__ void trpl_lse_init_kernel(double *out)
+{
+    out[0] = -INFINITY;
+    out[1] = 0.0;
+}
+
+// ---- FP64 FMA pipe microbenchmark ------------------------------------------------------------
+__global__ void trpl_dfma_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) out[0] = r;   // never true; keeps the chain alive
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return TRPL_ECUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
+    } while (0)
+
+// pvSimPCR.py:327-331 (same expression order; pow() is glibc's, as in CPython)
+void make_scales(double length, double time, int L, int T, double *sc, double *dx_o, double *dt_o)
+{
+    const double dx = length / L, dt = time / T;
+    const double dx3 = pow(dx, 3.0);
+    const double dtdx = dt / dx, dtdx2 = dtdx / dx, dtdx6 = dt / pow(dx, 6.0);
+    sc[0] = dx3; sc[1] = dx3; sc[2] = dtdx2; sc[3] = dtdx2; sc[4] = dtdx2 / dx;
+    sc[5] = dtdx; sc[6] = dtdx; sc[7] = dtdx6; sc[8] = dtdx6;
+    sc[9] = 1.0 / dt; sc[10] = 1.0 / dt; sc[11] = 1.0 / dx;
+    *dx_o = dx; *dt_o = dt;
+}
+
+struct Cfg { int M; bool pad; };
+int pick_cfg(int L, Cfg *cfg)
+{
+    if (L < 2) return TRPL_EINVAL;
+    int M = 1;
+    while (M <= 8 && 32 * M < L) M <<= 1;
+    if (M > 8) return TRPL_EUNSUPPORTED;          // L > 256: multi-warp simulations not built yet
+    if (L % M != 0 || L < 2 * M) return TRPL_EUNSUPPORTED;
+    cfg->M = M;
+    cfg->pad = (L != 32 * M);
+    return TRPL_OK;
+}
+
+typedef void (*kern_t)(const KArgs);
+kern_t pick_kernel(const Cfg &c)
+{
+    switch (c.M) {
+    case 1: return c.pad ? trpl_sim_kernel<1, true> : trpl_sim_kernel<1, false>;
+    case 2: return c.pad ? trpl_sim_kernel<2, true> : trpl_sim_kernel<2, false>;
+    case 4: return c.pad ? trpl_sim_kernel<4, true> : trpl_sim_kernel<4, false>;
+    default: return c.pad ? trpl_sim_kernel<8, true> : trpl_sim_kernel<8, false>;
+    }
+}
+
+int kernel_geometry(int device, const Cfg &cfg, kern_t *k_out, size_t *smem_out, int *ctas_per_sm,
+                    int *sms)
+{
+    kern_t k = pick_kernel(cfg);
+    const size_t smem = (size_t)WARPS_PER_CTA * 4 * 3 * cfg.M * 32 * sizeof(double);
+    CK(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k, WARPS_PER_CTA * 32, smem));
+    if (nb < 1) return TRPL_EUNSUPPORTED;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    *k_out = k; *smem_out = smem; *ctas_per_sm = nb; *sms = nsm;
+    return TRPL_OK;
+}
+
+int check_device(int device)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return TRPL_ENODEVICE;
+    }
+    CK(cudaSetDevice(device));
+    return TRPL_OK;
+}
+
+int launch_sims(KArgs &ka, const Cfg &cfg, int device, cudaStream_t st)
+{
+    kern_t k; size_t smem; int nb, nsm;
+    int rc = kernel_geometry(device, cfg, &k, &smem, &nb, &nsm);
+    if (rc) return rc;
+    unsigned long long *counter = nullptr;
+    CK(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    ka.counter = counter;
+    const unsigned long long items = (unsigned long long)ka.S * ka.C;
+    unsigned long long want = (items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    unsigned long long cap = (unsigned long long)nb * nsm;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (grid > 0) {
+        k<<<grid, WARPS_PER_CTA * 32, smem, st>>>(ka);
+        CK(cudaGetLastError());
+    }
+    CK(cudaFreeAsync(counter, st));
+    return TRPL_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int trpl_version(void) { return 100; }
+
+const char *trpl_error_string(int code)
+{
+    switch (code) {
+    case TRPL_OK: return "ok";
+    case TRPL_EINVAL: return "invalid argument";
+    case TRPL_EUNSUPPORTED: return "unsupported shape (need L = M*g, M in {1,2,4,8}, 2 <= g <= 32; "
+                                   "curves <= 8, observation files <= 4)";
+    case TRPL_ECUDA: return "CUDA runtime error";
+    case TRPL_ENODEVICE: return "no usable CUDA device";
+    default: return "unknown error";
+    }
+}
+
+const char *trpl_last_cuda_error(void) { return g_cuda_err; }
+
+int trpl_resident_sims(int device, int L)
+{
+    Cfg cfg;
+    int rc = pick_cfg(L, &cfg);
+    if (rc) return rc;
+    rc = check_device(device);
+    if (rc) return rc;
+    kern_t k; size_t smem; int nb, nsm;
+    rc = kernel_geometry(device, cfg, &k, &smem, &nb, &nsm);
+    if (rc) return rc;
+    return nb * nsm * WARPS_PER_CTA;
+}
+
+int trpl_solve_pl(const double *d_matpar, int64_t S, int64_t ld_matpar, const double *d_init,
+                  double length, double time, int L, int T, int plT, int tol, int max_iter,
+                  int max_order, int flags, void *d_pl, int pl_dtype, int64_t pl_stride,
+                  int32_t *d_status, int64_t *d_iters, int device, void *stream)
+{
+    if (!d_matpar || !d_init || !d_pl || S < 0 || ld_matpar < TRPL_NPAR || T < 1 || plT < 1 ||
+        max_iter < 1 || !(length > 0) || !(time > 0) || pl_stride < T / plT + 1 ||
+        (pl_dtype != TRPL_F64 && pl_dtype != TRPL_F32))
+        return TRPL_EINVAL;
+    Cfg cfg;
+    int rc = pick_cfg(L, &cfg);
+    if (rc) return rc;
+    rc = check_device(device);
+    if (rc) return rc;
+    if (S == 0) return TRPL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_order < 1 || max_order > 5) max_order = 5;
+
+    KArgs ka;
+    memset(&ka, 0, sizeof(ka));
+    ka.x = d_matpar; ka.ldx = ld_matpar; ka.S = S; ka.pl_stride = pl_stride;
+    ka.TOL = pow(10.0, -(double)tol);
+    ka.sse = nullptr; ka.status = d_status; ka.iters = (long long *)d_iters;
+    ka.mag_col = -1; ka.C = 1; ka.E = 0; ka.L = L; ka.plT = plT; ka.max_iter = max_iter;
+    ka.max_order = max_order;
+    ka.flags = (flags & TRPL_F_INIT_GRID_UNITS) | (pl_dtype == TRPL_F32 ? TRPL_F_EMULATE_F32 : 0);
+    ka.pl_dtype = pl_dtype;
+    CurveDev &cv = ka.curves[0];
+    double dx, dt;
+    make_scales(length, time, L, T, cv.scales, &dx, &dt);
+    cv.init_mul = (flags & TRPL_F_INIT_GRID_UNITS) ? 1.0 : cv.scales[0];
+    cv.redim = pow(dx, 2.0) * dt;
+    cv.init = d_init;
+    cv.pl_out = d_pl;
+    cv.t_last = T;
+    return launch_sims(ka, cfg, device, st);
+}
+
+int trpl_solve_loglik(const double *d_x, int64_t S, int64_t ldx, int mag_col,
+                      const trpl_curve *curves, int C, int E, double time, int L, int T, int tol,
+                      int max_iter, int max_order, int flags, double *d_sse, double *d_lnl,
+                      int32_t *d_status, int64_t *d_iters, int device, void *stream)
+{
+    if (!d_x || !curves || !d_sse || !d_lnl || S < 0 || ldx < TRPL_NPAR || mag_col >= ldx ||
+        T < 1 || max_iter < 1 || !(time > 0) || C < 1 || E < 1)
+        return TRPL_EINVAL;
+    if (C > TRPL_MAX_CURVES || E > TRPL_MAX_EXP) return TRPL_EUNSUPPORTED;
+    Cfg cfg;
+    int rc = pick_cfg(L, &cfg);
+    if (rc) return rc;
+    rc = check_device(device);
+    if (rc) return rc;
+    if (S == 0) return TRPL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_order < 1 || max_order > 5) max_order = 5;
+
+    KArgs ka;
+    memset(&ka, 0, sizeof(ka));
+    ka.x = d_x; ka.ldx = ldx; ka.S = S; ka.pl_stride = 0;
+    ka.TOL = pow(10.0, -(double)tol);
+    ka.sse = d_sse; ka.iters = (long long *)d_iters;
+    ka.mag_col = mag_col; ka.C = C; ka.E = E; ka.L = L; ka.plT = 1; ka.max_iter = max_iter;
+    ka.max_order = max_order; ka.flags = flags; ka.pl_dtype = TRPL_F64;
+    int *status_cs = nullptr;
+    if (d_status) CK(cudaMallocAsync((void **)&status_cs, sizeof(int) * (size_t)C * S, st));
+    ka.status = status_cs;
+    for (int c = 0; c < C; c++) {
+        const trpl_curve &src = curves[c];
+        if (!src.d_init || !(src.length > 0)) return TRPL_EINVAL;
+        CurveDev &cv = ka.curves[c];
+        double dx, dt;
+        make_scales(src.length, time, L, T, cv.scales, &dx, &dt);
+        cv.init_mul = (flags & TRPL_F_INIT_GRID_UNITS) ? 1.0 : cv.scales[0];
+        cv.redim = pow(dx, 2.0) * dt;
+        cv.init = src.d_init;
+        cv.pl_out = nullptr;
+        cv.t_last = 0;
+        for (int e = 0; e < E; e++) {
+            const trpl_obs &o = src.obs[e];
+            if (o.n < 0 || (o.n > 0 && (!o.d_hi || !o.d_whi || !o.d_wlo || !o.d_val)))
+                return TRPL_EINVAL;
+            if (o.n > 0 && (o.hi_max < 1 || o.hi_max > T)) return TRPL_EINVAL;
+            cv.obs[e].n = o.n; cv.obs[e].hi = o.d_hi; cv.obs[e].whi = o.d_whi;
+            cv.obs[e].wlo = o.d_wlo; cv.obs[e].val = o.d_val;
+            if (o.n > 0 && o.hi_max > cv.t_last) cv.t_last = o.hi_max;   // causal truncation
+        }
+    }
+    rc = launch_sims(ka, cfg, device, st);
+    if (rc) return rc;
+    const int tb = 256;
+    trpl_finish_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, st>>>(d_sse, d_lnl, status_cs, d_status,
+                                                                      S, C, E);
+    CK(cudaGetLastError());
+    if (status_cs) CK(cudaFreeAsync(status_cs, st));
+    return TRPL_OK;
+}
+
+int trpl_log10_clamp(void *d_pl, int dtype, int64_t n, double min, int device, void *stream)
+{
+    if (!d_pl || n < 0 || (dtype != TRPL_F64 && dtype != TRPL_F32)) return TRPL_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n == 0) return TRPL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    const int tb = 256;
+    long long blocks = (n + tb - 1) / tb;
+    if (blocks > (long long)nsm * 16) blocks = (long long)nsm * 16;
+    if (dtype == TRPL_F64)
+        trpl_log10_kernel_f64<<<(unsigned)blocks, tb, 0, st>>>((double *)d_pl, n, min);
+    else
+        trpl_log10_kernel_f32<<<(unsigned)blocks, tb, 0, st>>>((float *)d_pl, n, min);
+    CK(cudaGetLastError());
+    return TRPL_OK;
+}
+
+int trpl_lnp_accumulate(double *d_P, const double *d_pl, int64_t S, int64_t n, int64_t ld,
+                        const double *d_values, const double *d_mag, int device, void *stream)
+{
+    if (!d_P || !d_pl || !d_values || !d_mag || S < 0 || n < 0 || ld < n) return TRPL_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (S == 0) return TRPL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    const int tb = 256;
+    long long blocks = (S * 32 + tb - 1) / tb;
+    if (blocks > (long long)nsm * 8) blocks = (long long)nsm * 8;
+    trpl_lnp_kernel<<<(unsigned)blocks, tb, 0, st>>>(d_P, d_pl, S, n, ld, d_values, d_mag);
+    CK(cudaGetLastError());
+    return TRPL_OK;
+}
+
+int trpl_obs_prepare(const double *times, int32_t n, double time, int T, int32_t *hi, double *whi,
+                     double *wlo)
+{
+    if (!times || !hi || !whi || !wlo || n < 0 || T < 1 || !(time > 0)) return TRPL_EINVAL;
+    // numpy.linspace(0, time, T+1): x_i = i*step with step = time/T, and x_T = time exactly
+    const double step = time / T;
+    int maxhi = 0;
+    double prev = -INFINITY;
+    for (int32_t i = 0; i < n; i++) {
+        const double t = times[i];
+        if (!(t >= 0.0) || !(t <= time) || t < prev) return TRPL_EINVAL;
+        prev = t;
+        // searchsorted(side='left'): first index k with x_k >= t
+        long long k = (long long)floor(t / step);
+        if (k < 0) k = 0;
+        if (k > T) k = T;
+        auto xk = [&](long long q) { return q >= T ? time : (double)q * step; };
+        while (k > 0 && xk(k - 1) >= t) k--;
+        while (k < T && xk(k) < t) k++;
+        if (k < 1) k = 1;
+        if (k > T) k = T;
+        hi[i] = (int32_t)k;
+        const double x_lo = xk(k - 1), x_hi = xk(k);
+        whi[i] = (t - x_lo) / (x_hi - x_lo);
+        wlo[i] = (x_hi - t) / (x_hi - x_lo);
+        if (k > maxhi) maxhi = (int)k;
+    }
+    return maxhi;
+}
+
+int trpl_lse_partial(const double *d_x, int64_t n, double *d_out2, int device, void *stream)
+{
+    if (!d_x || !d_out2 || n < 0) return TRPL_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    trpl_lse_init_kernel<<<1, 1, 0, st>>>(d_out2);
+    if (n > 0) {
+        int nsm = 0;
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+        const int tb = 256;
+        long long blocks = (n + tb - 1) / tb;
+        if (blocks > (long long)nsm * 8) blocks = (long long)nsm * 8;
+        trpl_lse_max_kernel<<<(unsigned)blocks, tb, 0, st>>>(d_x, n, d_out2);
+        trpl_lse_sum_kernel<<<(unsigned)blocks, tb, 0, st>>>(d_x, n, d_out2);
+    }
+    CK(cudaGetLastError());
+    return TRPL_OK;
+}
+
+int trpl_bench_dfma(int device, int iters, double *tflops, double *ms)
+{
+    if (!tflops || iters < 1) return TRPL_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    double *out = nullptr;
+    CK(cudaMalloc((void **)&out, sizeof(double)));
+    const int tb = 256, blocks = nsm * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    trpl_dfma_kernel<<<blocks, tb>>>(out, iters / 4 + 1, 1.0);   // warm-up
+    CK(cudaEventRecord(e0));
+    trpl_dfma_kernel<<<blocks, tb>>>(out, iters, 1.0);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    const double flop = 2.0 * 8 * 16 * (double)iters * tb * (double)blocks;
+    *tflops = flop / (t * 1e-3) / 1e12;
+    if (ms) *ms = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return TRPL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+"""Shared test inputs: unit conversions and priors of the reference entry script
+(parallel_bayes_gpu.py:27-33,86,91-92), the shipped excitation profiles, golden loaders."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+UC = np.array([(1e7) ** -3, (1e7) ** -3,
+               (1e7) ** 2 / (1e9) * .02569257, (1e7) ** 2 / (1e9) * .02569257,
+               (1e7) ** 3 / (1e9), (1e7) / (1e9), (1e7) / (1e9),
+               (1e7) ** 6 / (1e9), (1e7) ** 6 / (1e9), 1, 1, 704.3, 1])
+TRUTH = np.array([1e8, 3e15, 20, 20, 4.8e-11, 10, 10, 4.4e-29, 4.4e-29, 511, 871, 0.1, 0])
+DO_LOG = np.array([1, 1, 0, 0, 1, 1, 1, 1, 1, 0, 0, 1, 0])
+MINX = np.array([1e8, 1e14, 0, 0, 1e-11, 0.1, 0.1, 1e-30, 1e-30, 1, 1, 10 ** -1, 0])
+MAXX = np.array([1e8, 1e16, 50, 50, 1e-9, 100, 100, 1e-28, 1e-28, 1000, 2000, 10 ** -1, 0])
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=True)
+
+
+def example_data():
+    return golden("example_data.npz")
+
+
+def power_scan_excitations():
+    """[3,128] nm^-3 (bayes_io.get_initpoints scaling 1e-21)."""
+    return example_data()["power_exc"] * 1e-21
+
+
+def prior_samples(n, seed, stiff=False, mag=False):
+    """Default prior of the entry script (physical engine units); mobilities start at 0.5 instead
+    of 0 to keep D > 0."""
+    rng = np.random.default_rng(seed)
+    lo, hi = MINX.copy(), MAXX.copy()
+    lo[2:4] = 0.5
+    if stiff:
+        lo[5:7], hi[5:7] = 1.0, 1e5
+    if mag:
+        lo[12], hi[12] = -0.5, 0.5
+    X = np.empty((n, 13))
+    for j in range(13):
+        if lo[j] == hi[j]:
+            X[:, j] = lo[j]
+        elif DO_LOG[j]:
+            X[:, j] = 10 ** rng.uniform(np.log10(lo[j]), np.log10(hi[j]), n)
+        else:
+            X[:, j] = rng.uniform(lo[j], hi[j], n)
+    return X * UC
+
+
+def pl_noise_floor(matpar_phys, length, time, L, T):
+    """Absolute rounding floor of PL = rate*(sum N*P - L*N0*P0)/(dx^2 dt): the two terms cancel,
+    so any summation order leaves ~L*eps*N0*P0*rate of noise (pvSimPCR.py:278-281)."""
+    dx, dt = length / L, time / T
+    n0, p0, B = matpar_phys[:, 0], matpar_phys[:, 1], matpar_phys[:, 4]
+    return 64 * np.finfo(float).eps * L * (n0 * dx ** 3) * (p0 * dx ** 3) * (B * dt / dx ** 3) / (dx ** 2 * dt)
+
+
+def simpar_from_golden(g):
+    length, Time, L, T, plT, tol, MAX = g["simPar"]
+    return [float(length), float(Time), int(L), int(T), int(plT), (0,), int(tol), int(MAX)]

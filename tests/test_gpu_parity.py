@@ -1,0 +1,289 @@
+"""GPU parity tests (run on the B200 box): the sm_100a kernels, reached through the C ABI, against
+the CPU oracle (oracle/) and the committed reference goldens.  Tolerances:
+  PL      rtol 1e-6 (north_star) + the absolute rounding floor of the PL cancellation; in
+          practice agreement is ~1e-12 unless a Newton stop decision flips;
+  lnL     rtol 1e-6 on samples whose PL stays above that floor.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import (GOLDEN, TRUTH, UC, example_data, golden, pl_noise_floor, power_scan_excitations,
+                     prior_samples, simpar_from_golden)
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def trpl():
+    import bayesian_inference_trpl_b200 as t
+    assert os.path.exists(t._lib.LIB_PATH), "libtrpl_b200.so must ship with the snapshot"
+    t._lib.lib()
+    return t
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as o
+    return o
+
+
+def _assert_pl_close(pl, ref, mat, simPar, rtol=1e-6):
+    floor = pl_noise_floor(mat, simPar[0], simPar[1], simPar[2], simPar[3])[:, None]
+    err = np.abs(pl - ref)
+    ok = err <= rtol * np.abs(ref) + floor
+    assert ok.all(), "max rel err %.3e at %s" % (np.nanmax(err / np.abs(ref)), np.argwhere(~ok)[:5])
+
+
+# ------------------------------------------------------------------------------------------------
+# forward model: reference goldens (tiny shapes the numba simulator can run)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["pvsim_points_f64", "pvsim_points_f32", "pvsim_exp_f64",
+                                  "pvsim_stiff_f64"])
+def test_pvsim_dropin_matches_reference_golden(trpl, name):
+    path = os.path.join(GOLDEN, "cudasim_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    g = golden("cudasim_%s.npz" % name)
+    simPar = simpar_from_golden(g)
+    mode = str(g["init_mode"])
+    ini = g["iniPar"].copy() if mode == "points" else list(g["iniPar"])
+    ref = g["pl"]
+    pl = np.empty_like(ref)
+    mat = g["matPar"].copy()
+    secs = trpl.pvSim(pl, None, None, None, mat, simPar, ini, (simPar[2],), 8, 1, init_mode=mode)
+    assert isinstance(secs, float) and secs >= 0
+    np.testing.assert_array_equal(mat, g["matPar"])          # inputs untouched
+    if ref.dtype == np.float32:
+        np.testing.assert_allclose(pl, ref, rtol=2.5e-7)      # <= 2 ulp of float32
+    else:
+        np.testing.assert_allclose(pl, ref, rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+# forward model vs oracle at real grid sizes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,length", [(128, 2000.0), (128, 311.0), (64, 1000.0), (32, 500.0),
+                                      (256, 2000.0), (96, 1500.0), (16, 250.0), (8, 125.0)])
+def test_solve_pl_matches_oracle(trpl, oracle, L, length):
+    T = 1500 if L <= 128 else 400
+    Time = 0.025 * T
+    simPar = [length, Time, L, T, 1, (0,), 7, 10000]
+    X = prior_samples(6, seed=L, stiff=(length < 400))
+    X[0] = TRUTH * UC
+    x = (np.arange(L) + 0.5) * (length / L)
+    for amp in (1.2738e16, 1.6485e18):
+        ini = amp * 1e-21 * np.exp(-6e-3 * x)
+        ref = oracle.solve(X[:, :12], simPar, ini, solver="pcr" if (L & (L - 1)) == 0 else "thomas")
+        pl = np.empty((len(X), T + 1))
+        st = np.zeros(len(X), dtype=np.int32)
+        trpl.pvSim(pl, None, None, None, X[:, :12], simPar, ini, (128,), 0, 1, init_mode="points",
+                   status_out=st)
+        assert (st == 0).all() and (ref["status"] == 0).all()
+        _assert_pl_close(pl, ref["pl"], X[:, :12], simPar)
+
+
+def test_iteration_counts_and_status_match_oracle(trpl, oracle):
+    L, T, length = 128, 800, 2000.0
+    simPar = [length, 0.025 * T, L, T, 1, (0,), 7, 10000]
+    X = prior_samples(16, seed=3)
+    ini = power_scan_excitations()[2]
+    ref = oracle.solve(X[:, :12], simPar, ini, solver="pcr")
+    dev = torch.device("cuda", 0)
+    mat = torch.from_numpy(np.ascontiguousarray(X[:, :12])).to(dev)
+    pl, status, iters = trpl.engine.solve_pl(mat, torch.from_numpy(ini).to(dev), length, simPar[1],
+                                            L, T)
+    torch.cuda.synchronize()
+    it = iters.cpu().numpy()
+    assert (status.cpu().numpy() == 0).all()
+    # identical stop decisions except (rarely) on a knife edge
+    assert np.abs(it - ref["iters"]).max() <= 2, (it, ref["iters"])
+    assert (it == ref["iters"]).mean() >= 0.8
+
+
+def test_nonconvergence_is_reported_per_sample(trpl, oracle):
+    L, T, length = 32, 40, 500.0
+    simPar = [length, 0.025 * T, L, T, 1, (0,), 12, 3]     # tol 1e-12 within 3 iterations: fails
+    X = prior_samples(4, seed=9)
+    x = (np.arange(L) + 0.5) * (length / L)
+    ini = 1.6e18 * 1e-21 * np.exp(-6e-3 * x)
+    ref = oracle.solve(X[:, :12], simPar, ini, solver="pcr")
+    pl = np.zeros((4, T + 1))
+    st = np.zeros(4, dtype=np.int32)
+    trpl.pvSim(pl, None, None, None, X[:, :12], simPar, ini, (32,), 0, 1, init_mode="points",
+               status_out=st)
+    np.testing.assert_array_equal(st & 1, ref["status"] & 1)
+    assert (st & 1).any()
+    np.testing.assert_array_equal(np.isnan(pl), np.isnan(ref["pl"]))
+    good = ~np.isnan(pl)
+    np.testing.assert_allclose(pl[good], ref["pl"][good], rtol=1e-9)
+
+
+def test_plT_stride_and_legacy_order(trpl, oracle):
+    L, T, plT, length = 64, 303, 4, 800.0
+    simPar = [length, 0.025 * T, L, T, plT, (0,), 7, 10000]
+    X = prior_samples(3, seed=5)
+    x = (np.arange(L) + 0.5) * (length / L)
+    ini = 1.1e17 * 1e-21 * np.exp(-6e-3 * x)
+    ref = oracle.solve(X[:, :12], simPar, ini, solver="pcr")
+    pl = np.empty((3, T // plT + 1))
+    trpl.pvSim(pl, None, None, None, X[:, :12], simPar, ini, (64,), 0, 1, init_mode="points")
+    np.testing.assert_allclose(pl, ref["pl"], rtol=1e-8)
+    # BDF order cap 2 (Legacy/pvSim.py) through the device API
+    dev = torch.device("cuda", 0)
+    ref2 = oracle.solve(X[:, :12], simPar, ini, solver="thomas", max_order=2)
+    pl2, _, _ = trpl.engine.solve_pl(torch.from_numpy(np.ascontiguousarray(X[:, :12])).to(dev),
+                                     torch.from_numpy(ini).to(dev), length, simPar[1], L, T, plT,
+                                     max_order=2)
+    np.testing.assert_allclose(pl2.cpu().numpy(), ref2["pl"], rtol=1e-8)
+
+
+def test_full_length_power_scan_curve(trpl, oracle):
+    """BASELINE config shape: L=128, T=80000 (2000 ns), tol 7 -- truth sample, all 3 curves."""
+    L, T, length = 128, 80000, 2000.0
+    simPar = [length, 2000.0, L, T, 1, (0,), 7, 10000]
+    X = prior_samples(2, seed=21)
+    X[0] = TRUTH * UC
+    inis = power_scan_excitations()
+    for c in range(3):
+        ref = oracle.solve(X[:, :12], simPar, inis[c], solver="thomas")
+        pl = np.empty((2, T + 1))
+        trpl.pvSim(pl, None, None, None, X[:, :12], simPar, inis[c], (128,), 0, 1, init_mode="points")
+        _assert_pl_close(pl, ref["pl"], X[:, :12], simPar)
+        # Testing/compare.py metric: relative L2 error of PL at 6 sample times
+        m = T + 1
+        tt = np.array([0 * m, 0.01 * m, 0.03 * m, 0.1 * m, 0.3 * m, m - 1], dtype=int)
+        for s in range(2):
+            nerr = np.linalg.norm(pl[s, tt] - ref["pl"][s, tt]) / np.linalg.norm(ref["pl"][s, tt])
+            assert nerr < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------
+# likelihood pieces
+# ------------------------------------------------------------------------------------------------
+def test_probs_dropins_match_reference_golden(trpl):
+    g = golden("cudasim_probs.npz")
+    P = g["P_in"].copy()
+    secs = trpl.prob(P, g["pli"], g["values"], g["unc"], g["mag"], 128, 148)
+    assert isinstance(secs, float)
+    np.testing.assert_allclose(P, g["P_out"], rtol=1e-12)
+    x = g["log_in64"].copy()
+    trpl.fastlog(x, float(g["MIN"]), 128, 148)
+    np.testing.assert_allclose(x, g["log_out64"], rtol=1e-14, atol=1e-13)
+    x32 = g["log_in32"].copy()
+    trpl.fastlog(x32, float(g["MIN"]), 128, 148)
+    np.testing.assert_allclose(x32, g["log_out32"], rtol=3e-7, atol=1e-7)
+    z = np.array([[0.0, -1.0, 1e-310, 1.0]], dtype=np.float32)
+    trpl.fastlog(z, sys.float_info.min, 128, 148)
+    assert np.isneginf(z[0, :3]).all() and z[0, 3] == 0.0
+
+
+def test_prob_large_random(trpl, oracle):
+    rng = np.random.default_rng(2)
+    S, n = 300, 5001
+    pli = rng.uniform(-12, -5, (S, n))
+    values = rng.uniform(-12, -5, n)
+    mag = rng.uniform(-1, 1, S)
+    P = np.zeros(S)
+    Pr = np.zeros(S)
+    trpl.prob(P, pli, values, np.ones(n), mag, 128, 148)
+    oracle.prob(Pr, pli, values, mag)
+    np.testing.assert_allclose(P, Pr, rtol=1e-12)
+
+
+def _synthetic_edata(oracle, simPar, inis, lengths, rng, n_exp=1, every=(1, 3, 7), offgrid=False):
+    """Observations = oracle PL of the truth sample (+ small deterministic wiggle), log10."""
+    Time, L, T = simPar[1], simPar[2], simPar[3]
+    e_data = []
+    for e in range(n_exp):
+        ts, vs, us = [], [], []
+        for c in range(len(inis)):
+            sp = list(simPar); sp[0] = lengths[c]
+            pl = oracle.solve((TRUTH * UC)[None, :12], sp, inis[c], solver="thomas")["pl"][0]
+            grid = np.linspace(0, Time, T + 1)
+            idx = np.arange(0, T + 1 - 5 * e, every[(c + e) % len(every)])
+            t = grid[idx].copy()
+            v = np.log10(pl[idx]) + 0.01 * np.sin(idx / 50.0 + e)
+            if offgrid:
+                t = np.sort(np.clip(t + rng.uniform(-0.4, 0.4, len(t)) * Time / T, 0, Time))
+            ts.append(t); vs.append(v); us.append(np.full(len(t), 0.1))
+        e_data.append((ts, vs, us))
+    return e_data
+
+
+@pytest.mark.parametrize("emulate_f32,normalize,log_pl,offgrid,n_exp",
+                         [(False, False, True, False, 1), (True, False, True, False, 1),
+                          (False, True, True, True, 2), (True, True, True, False, 1),
+                          (False, False, False, True, 1)])
+def test_fused_loglik_matches_oracle_pipeline(trpl, oracle, emulate_f32, normalize, log_pl, offgrid,
+                                              n_exp):
+    rng = np.random.default_rng(4)
+    L, T = 128, 600
+    lengths = [2000.0, 311.0, 2000.0]
+    simPar = [lengths, 0.025 * T, L, T, 1, (0,), 7, 10000]
+    inis = power_scan_excitations()
+    e_data = _synthetic_edata(oracle, simPar, inis, lengths, rng, n_exp=n_exp, offgrid=offgrid)
+    if not log_pl:
+        e_data = [(ts, [10 ** v for v in vs], us) for ts, vs, us in e_data]
+    X = prior_samples(24, seed=8, mag=True)
+    X[0] = TRUTH * UC
+    ref = oracle.loglik(X, simPar, inis, e_data, log_pl=log_pl, self_normalize=normalize,
+                        emulate_f32=emulate_f32, solver="pcr")
+    dev = torch.device("cuda", 0)
+    prob = trpl.engine.Problem(simPar, inis, e_data, device=0)
+    Xd = torch.from_numpy(X).to(dev)
+    lnl, status, iters = trpl.engine.solve_loglik(Xd, prob, log_pl=log_pl, self_normalize=normalize,
+                                                  emulate_f32=emulate_f32, want_iters=True)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    got = lnl.cpu().numpy()
+    assert got.shape == ref.shape == (n_exp, len(X))
+    rtol = 1e-6 if not emulate_f32 else 2e-5       # log10f vs float64 log10 rounded (1 ulp f32)
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=1e-9)
+    # accumulate semantics (probs.py:60): a second call adds to the table
+    lnl2, _, _ = trpl.engine.solve_loglik(Xd, prob, log_pl=log_pl, self_normalize=normalize,
+                                          emulate_f32=emulate_f32, lnl=lnl.clone())
+    np.testing.assert_allclose(lnl2.cpu().numpy(), 2 * got, rtol=1e-12)
+
+
+def test_bayes_mirror_matches_reference_bayes_golden(trpl):
+    """Unmodified reference bayeslib.bayes (simulator run) vs this package's bayes(): same seed,
+    same sample matrix, likelihood table within float32-pipeline tolerance."""
+    path = os.path.join(GOLDEN, "cudasim_bayes.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    g = golden("cudasim_bayes.npz")
+    L, T = int(g["L"]), int(g["T"])
+    simPar = [list(g["length"]), float(g["Time"]), L, T, 1, (0,), 7, 10000]
+    e_data = [(list(g["t_obs"]), list(g["v_obs"]), list(g["u_obs"]))]
+    sim_flags = {"load_PL_from_file": False, "override_equal_auger": False,
+                 "override_equal_mu": False, "override_equal_s": True, "log_pl": True,
+                 "self_normalize": False, "random_sample": True, "num_points": len(g["X"])}
+    for fused, emu in ((True, True), (False, False), (True, False)):
+        gpu_info = {"sims_per_gpu": 2, "num_gpus": 1, "fused": fused, "emulate_f32": emu}
+        trpl.bayes_validate.connect_to_gpu(gpu_info, nthreads=128, sims_per_block=1)
+        np.random.seed(42)
+        N, P, X = trpl.bayeslib.bayes(trpl.pvSim, np.array([0]), None, g["minX"], g["maxX"],
+                                      g["do_log"], g["iniPar"], list(simPar), e_data, sim_flags,
+                                      gpu_info)
+        np.testing.assert_array_equal(X, g["X"])
+        np.testing.assert_allclose(P, g["P"], rtol=2e-5 if (emu or not fused) else 1e-4)
+
+
+def test_lse_partial_matches_numpy(trpl):
+    rng = np.random.default_rng(6)
+    x = rng.normal(-5000, 2000, 100003)
+    x[5] = np.nan
+    out = trpl.engine.lse_partial(torch.from_numpy(x).cuda()).cpu().numpy()
+    m = np.nanmax(x)
+    assert out[0] == m
+    np.testing.assert_allclose(out[1], np.nansum(np.exp(x - m)), rtol=1e-12)
+
+
+def test_dfma_microbenchmark_runs(trpl):
+    tf, ms = trpl.engine.bench_dfma(2000)
+    assert 1.0 < tf < 100.0
