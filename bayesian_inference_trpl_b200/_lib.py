@@ -9,7 +9,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libtrpl_b200.so")
+LIB_PATH = os.environ.get("TRPL_LIB", os.path.join(_PKG, "libtrpl_b200.so"))   # TRPL_LIB: A/B-test builds
 SRC = os.path.join(_PKG, "csrc", "trpl_kernels.cu")
 INCLUDE = os.path.join(_ROOT, "include")
 

@@ -38,6 +38,9 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS_PER_CTA = 4;
+#ifndef TRPL_MIN_CTAS
+#define TRPL_MIN_CTAS 4
+#endif
 
 struct ObsDev {
     int n;
@@ -79,16 +82,15 @@ struct KArgs {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double rcp64(double x)
 {
-    // MUFU.RCP64H seed + cubic step + one Newton step (no slow path: operands here are
-    // normal, finite and far from the exponent limits).
+    // MUFU.RCP64H seed (rel. error <= 1e-6, measured on B200 with tools/microbench.cu) followed by
+    // one cubically convergent step r*(1 + e + e^2): max error 1 ulp (2.2e-16, measured over 2^24
+    // operands in four magnitude ranges).  No slow path: operands here are normal, finite and far
+    // from the exponent limits.
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = fma(-x, r, 1.0);
     e = fma(e, e, e);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    return fma(r, e, r);
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -112,17 +114,28 @@ __device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double
     double c[M > 1 ? M - 1 : 1], y[M > 1 ? M - 1 : 1], v[M > 1 ? M - 1 : 1], w[M > 1 ? M - 1 : 1];
     if constexpr (M > 1) {
         // interior rows 0..M-2:  x_j = y_j - v_j * s_left - w_j * s_own
-        double inv = rcp64(d[0]);
-        c[0] = u[0] * inv;
-        y[0] = b[0] * inv;
-        v[0] = l[0] * inv;
+        // Pivot reciprocals from the leading principal minors m_{j+1} = d_j m_j - l_j u_{j-1} m_{j-1}
+        // (1/pivot_j = m_j / m_{j+1}): the M-1 reciprocals are independent of each other, so
+        // their MUFU+Newton chains overlap instead of forming one serial chain.
+        double ip[M - 1];
+        {
+            double mm[M];                 // mm[j] = m_{j+1}
+            mm[0] = d[0];
+            if constexpr (M > 2) mm[1] = fma(d[1], d[0], -(l[1] * u[0]));
+#pragma unroll
+            for (int j = 2; j < M - 1; j++) mm[j] = fma(d[j], mm[j - 1], -((l[j] * u[j - 1]) * mm[j - 2]));
+            ip[0] = rcp64(mm[0]);
+#pragma unroll
+            for (int j = 1; j < M - 1; j++) ip[j] = mm[j - 1] * rcp64(mm[j]);
+        }
+        c[0] = u[0] * ip[0];
+        y[0] = b[0] * ip[0];
+        v[0] = l[0] * ip[0];
 #pragma unroll
         for (int j = 1; j < M - 1; j++) {
-            double den = fma(-l[j], c[j - 1], d[j]);
-            inv = rcp64(den);
-            c[j] = u[j] * inv;
-            y[j] = fma(-l[j], y[j - 1], b[j]) * inv;
-            v[j] = (-l[j] * v[j - 1]) * inv;
+            c[j] = u[j] * ip[j];
+            y[j] = fma(-l[j], y[j - 1], b[j]) * ip[j];
+            v[j] = (-l[j] * v[j - 1]) * ip[j];
         }
         w[M - 2] = c[M - 2];
 #pragma unroll
@@ -150,6 +163,12 @@ __device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double
     }
 #pragma unroll
     for (int rf = 1; rf < 32; rf <<= 1) {
+        // Off-diagonals shrink quadratically per stage; once every |L|,|U| of the warp is below
+        // 2^-70 the remaining stages cannot change D = 1 or B in the last bit: stop (warp-uniform).
+        if (rf >= 2) {
+            const int hl = __double2hiint(Lr) & 0x7fffffff, hu = __double2hiint(Ur) & 0x7fffffff;
+            if (__all_sync(FULL, max(hl, hu) < ((1023 - 70) << 20))) break;
+        }
         const double Lm = __shfl_up_sync(FULL, Lr, rf);
         const double Um = __shfl_up_sync(FULL, Ur, rf);
         const double Bm = __shfl_up_sync(FULL, Br, rf);
@@ -233,7 +252,9 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     const double tauN = __shfl_sync(FULL, mpl, 9), tauP = __shfl_sync(FULL, mpl, 10);
     const double Lam = __shfl_sync(FULL, mpl, 11);
     const double N0P0 = N0 * P0;
-    const double hDN = 0.5 * DN, hDP = 0.5 * DP, hLam = 0.5 * Lam;
+    const double hDN = 0.5 * DN, hDP = 0.5 * DP;
+    const double CN_N0P0 = CN * N0P0, CP_N0P0 = CP * N0P0;
+    const double LamDP = Lam * DP, LamDN = Lam * DN, hLamDP = 0.5 * LamDP, hLamDN = 0.5 * LamDN;
     const double TOL = a.TOL;
     const double mag = (a.mag_col >= 0) ? a.x[s * a.ldx + a.mag_col] : 0.0;
 
@@ -435,6 +456,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
         for (;;) {
             double l[M], d[M], u[M], b[M];
             double rN = 0.0, sbN = 0.0, rP = 0.0, sbP = 0.0;
+            bool converged_now = false, nonfinite_now = false;
 
             // ======== N system (P, E frozen) ========
             {
@@ -454,12 +476,13 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double r = rcp64(tp);
                     const double q = fma(-tauP, npp, Pj * tp);
                     const double srh = (q * r) * r;
-                    const double aug = fma(CP, Pj * Pj, CN * (NP + npp));
+                    const double cnN = CN * Nj;
+                    const double aug = fma(Pj, fma(CP, Pj, cnN + cnN), -CN_N0P0);   // CN*N*P + CP*P^2 + CN*np
                     const double nds = fma(rate, Pj, srh) + aug;             // = -ds
                     l[j] = cl[j];
                     u[j] = cu[j + 1];
                     d[j] = ((a0 - cu[j]) - cl[j + 1]) + nds;
-                    const double g = fma(CN, Nj, fma(CP, Pj, rate + r));
+                    const double g = fma(CP, Pj, cnN) + (rate + r);
                     b[j] = fma(nds, Nj, -fma(g, npp, bN[j]));
                 }
                 // surface recombination rows                                 (pvSimPCR.py:164-170)
@@ -515,12 +538,13 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double r = rcp64(tp);
                     const double q = fma(-tauN, npp, Nj * tp);
                     const double srh = (q * r) * r;
-                    const double aug = fma(CN, Nj * Nj, CP * (NP + npp));
+                    const double cpP = CP * Pj;
+                    const double aug = fma(Nj, fma(CN, Nj, cpP + cpP), -CP_N0P0);   // CP*N*P + CN*N^2 + CP*np
                     const double nds = fma(rate, Nj, srh) + aug;
                     l[j] = cl[j];
                     u[j] = cu[j + 1];
                     d[j] = ((a0 - cu[j]) - cl[j + 1]) + nds;
-                    const double g = fma(CN, Nj, fma(CP, Pj, rate + r));
+                    const double g = fma(CN, Nj, cpP) + (rate + r);
                     b[j] = fma(nds, Pj, -fma(g, npp, bP[j]));
                 }
                 {
@@ -551,6 +575,26 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     rP += fabs(res);
                     sbP += fabs(b[j]);
                 }
+                // ---- stop decision for THIS iteration (pvSimPCR.py:213-216): both L1 residuals are
+                // known here, before the P solve; reducing them now lets the shuffle chain overlap
+                // the solve.  Lanes 0-7 end up with errN, lanes 8-15 with errP.
+                {
+                    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+                    double k0 = hi16 ? sbN : rN, k1 = hi16 ? sbP : rP;
+                    const double s0 = hi16 ? rN : sbN, s1 = hi16 ? rP : sbP;
+                    k0 += __shfl_xor_sync(FULL, s0, 16);
+                    k1 += __shfl_xor_sync(FULL, s1, 16);
+                    double k = hi8 ? k1 : k0;
+                    const double sd = hi8 ? k0 : k1;
+                    k += __shfl_xor_sync(FULL, sd, 8);
+                    k += __shfl_xor_sync(FULL, k, 4);
+                    k += __shfl_xor_sync(FULL, k, 2);
+                    k += __shfl_xor_sync(FULL, k, 1);
+                    const double other = __shfl_xor_sync(FULL, k, 16);
+                    const double err = k * rcp64(other);
+                    converged_now = (__ballot_sync(FULL, err < TOL) & 0xffffu) == 0xffffu;
+                    nonfinite_now = (__ballot_sync(FULL, !(fabs(err) <= DBL_MAX)) & 0xffffu) != 0u;
+                }
                 tridiag_solve<M>(l, d, u, b, P);
                 Pl = __shfl_up_sync(FULL, P[M - 1], 1);
                 Pr = __shfl_down_sync(FULL, P[0], 1);
@@ -561,33 +605,16 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             for (int j = 0; j < M; j++) {
                 const double Nm = (j == 0) ? Nl : N[j - 1];
                 const double Pm = (j == 0) ? Pl : P[j - 1];
-                const double den = fma(hLam, fma(DP, P[j] + Pm, DN * (N[j] + Nm)), a0);
-                const double num = fma(Lam, fma(DP, P[j] - Pm, -(DN * (N[j] - Nm))), -bE[j]);
+                const double den = fma(hLamDP, P[j] + Pm, fma(hLamDN, N[j] + Nm, a0));
+                const double num = fma(LamDP, P[j] - Pm, fma(-LamDN, N[j] - Nm, -bE[j]));
                 E[j] = sel(ev[j], num * rcp64(den), 0.0);
             }
             En = __shfl_down_sync(FULL, E[0], 1);
 
-            // ======== convergence test on the residuals of the previous iterate (pvSimPCR.py:213-216)
+            // ======== stop rule (pvSimPCR.py:213-216): decided by the flags computed before the P solve
             it++;
-            {
-                const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
-                double k0 = hi16 ? sbN : rN, k1 = hi16 ? sbP : rP;
-                const double s0 = hi16 ? rN : sbN, s1 = hi16 ? rP : sbP;
-                k0 += __shfl_xor_sync(FULL, s0, 16);
-                k1 += __shfl_xor_sync(FULL, s1, 16);
-                double k = hi8 ? k1 : k0;
-                const double sd = hi8 ? k0 : k1;
-                k += __shfl_xor_sync(FULL, sd, 8);
-                k += __shfl_xor_sync(FULL, k, 4);
-                k += __shfl_xor_sync(FULL, k, 2);
-                k += __shfl_xor_sync(FULL, k, 1);
-                const double other = __shfl_xor_sync(FULL, k, 16);
-                const double err = k / other;                 // lanes 0-7: errN, lanes 8-15: errP
-                const unsigned okm = __ballot_sync(FULL, err < TOL) & 0xffffu;
-                const unsigned nfm = __ballot_sync(FULL, !(fabs(err) <= DBL_MAX)) & 0xffffu;
-                if (nfm) { nonfinite = true; break; }
-                if (okm == 0xffffu) break;
-            }
+            if (nonfinite_now) { nonfinite = true; break; }
+            if (converged_now) break;
             if (it >= a.max_iter) break;
         }
         iters_total += it;
@@ -629,7 +656,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
 }
 
 template <int M, bool PAD>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, TRPL_MIN_CTAS)
 trpl_sim_kernel(const __grid_constant__ KArgs a)
 {
     extern __shared__ __align__(16) double smem[];

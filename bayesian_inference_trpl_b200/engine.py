@@ -26,6 +26,11 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _row_stride(t):
+    # a single-row view may carry any (even 0) stride on its first axis
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
 def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
@@ -125,7 +130,7 @@ def solve_pl(matpar, init, length, time, L, T, plT=1, tol=7, max_iter=10000, out
     iters = torch.zeros(S, dtype=torch.int64, device=dev) if want_iters else None
     flags = F_INIT_GRID_UNITS if init_grid_units else 0
     rc = _lib.lib().trpl_solve_pl(
-        _ptr(matpar), S, matpar.stride(0), _ptr(init), float(length), float(time), int(L), int(T),
+        _ptr(matpar), S, _row_stride(matpar), _ptr(init), float(length), float(time), int(L), int(T),
         int(plT), int(tol), int(max_iter), int(max_order), flags, _ptr(pl),
         F32 if out_dtype == torch.float32 else F64, npl, _ptr(status), _ptr(iters),
         dev.index, _stream(dev))
@@ -153,7 +158,7 @@ def solve_loglik(X, problem, log_pl=True, self_normalize=False, emulate_f32=Fals
              | (F_EMULATE_F32 if emulate_f32 else 0))
     mag_col = 12 if X.shape[1] > 12 else -1
     rc = _lib.lib().trpl_solve_loglik(
-        _ptr(X), S, X.stride(0), mag_col, problem.curves, C, E, problem.Time, problem.L, problem.T,
+        _ptr(X), S, _row_stride(X), mag_col, problem.curves, C, E, problem.Time, problem.L, problem.T,
         problem.tol, problem.MAX, int(max_order), flags, _ptr(sse), _ptr(lnl), _ptr(status),
         _ptr(iters), dev.index, _stream(dev))
     check(rc, "trpl_solve_loglik")
