@@ -264,7 +264,9 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
 #pragma unroll
     for (int j = 0; j <= M; j++) {
         const int m = M * lane + j;
-        ev[j] = (m >= 1) && (m <= L - 1);
+        // exact-fit grids (L == 32*M): only edge 0 (lane 0) and edge L (lane 31) are boundaries,
+        // so the selects on the inner edges fold away at compile time
+        ev[j] = PAD ? ((m >= 1) && (m <= L - 1)) : (j == 0 ? (lane != 0) : (j == M ? (lane != 31) : true));
     }
     bool nv[M];                                // node n = M*lane + j exists
 #pragma unroll
