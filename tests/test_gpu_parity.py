@@ -287,3 +287,93 @@ def test_lse_partial_matches_numpy(trpl):
 def test_dfma_microbenchmark_runs(trpl):
     tf, ms = trpl.engine.bench_dfma(2000)
     assert 1.0 < tf < 100.0
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3 and 4 at reduced sample counts
+# ------------------------------------------------------------------------------------------------
+def _shipped_observations(name, t_max):
+    """(t_list, log10 PL list, unc list) from the condensed fixture of a shipped stiff-regime
+    observation file (every 25th point; values scaled like bayes_io.get_data, bayes_io.py:15)."""
+    ex = example_data()
+    ts, vs, us = [], [], []
+    for c in range(3):
+        t = ex["%s_t%d" % (name, c)]
+        v = ex["%s_pl%d" % (name, c)] * 1e-23
+        keep = t <= t_max
+        ts.append(t[keep]); vs.append(np.log10(v[keep])); us.append(np.full(keep.sum(), 0.1))
+    return (ts, vs, us)
+
+
+def test_config3_stiff_surface_regime_shipped_observations(trpl, oracle):
+    """Highfrontsurf / Highbacksurf / Balancedhighsurf observation files (3 files = 3 experiments
+    in one fused call), stiff prior Sf,Sb in [1, 1e5] cm/s, 100 ns window."""
+    L, T = 128, 4000
+    simPar = [2000.0, 0.025 * T, L, T, 1, (0,), 7, 10000]
+    inis = power_scan_excitations()
+    e_data = [_shipped_observations(n, simPar[1]) for n in
+              ("Highfrontsurf", "Highbacksurf", "Balancedhighsurf")]
+    X = prior_samples(20, seed=31, stiff=True)
+    for k, (sf, sb) in enumerate(((1e4, 10), (10, 1e4), (5e3, 5e3))):      # identified truths
+        x = TRUTH.copy(); x[5], x[6] = sf, sb
+        X[k] = x * UC
+    ref = oracle.loglik(X, simPar, inis, e_data, solver="pcr")
+    prob = trpl.engine.Problem(simPar, inis, e_data, device=0)
+    lnl, status, _ = trpl.engine.solve_loglik(torch.from_numpy(X).cuda(), prob)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    got = lnl.cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-9)
+    # each truth sample is the most likely one for "its" file among the 20
+    for e in range(3):
+        assert np.argmax(got[e]) == e
+
+
+def test_config4_two_thickness_six_curves(trpl, oracle):
+    """Twothick excitations: 6 curves alternating 311 nm / 2000 nm."""
+    ex = example_data()
+    inis = ex["twothick_exc"] * 1e-21
+    lengths = [311.0, 2000.0] * 3
+    L, T = 128, 500
+    simPar = [lengths, 0.025 * T, L, T, 1, (0,), 7, 10000]
+    rng = np.random.default_rng(12)
+    e_data = _synthetic_edata(oracle, simPar, inis, lengths, rng, n_exp=1, every=(1, 2, 5))
+    X = prior_samples(10, seed=41)
+    X[0] = TRUTH * UC
+    ref = oracle.loglik(X, simPar, inis, e_data, solver="pcr")
+    prob = trpl.engine.Problem(simPar, inis, e_data, device=0)
+    lnl, status, iters = trpl.engine.solve_loglik(torch.from_numpy(X).cuda(), prob, want_iters=True)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    assert iters.shape == (6, 10)
+    np.testing.assert_allclose(lnl.cpu().numpy(), ref, rtol=1e-6, atol=1e-9)
+    assert np.argmax(lnl.cpu().numpy()[0]) == 0
+
+
+def test_likelihood_properties_at_full_size(trpl):
+    """BASELINE-size property checks that need no oracle run: lnL <= 0, the generating sample
+    scores exactly like itself (lnL = 0 up to rounding), mag_offset shifts add n*m^2-type terms
+    consistently, and two identical rows give bit-identical results (determinism)."""
+    L, T = 128, 80000
+    simPar = [2000.0, 2000.0, L, T, 1, (0,), 7, 10000]
+    inis = power_scan_excitations()
+    truth = (TRUTH * UC)
+    grid = np.linspace(0, 2000.0, T + 1)
+    ts, vs, us = [], [], []
+    for c in range(3):
+        pl = np.empty((1, T + 1))
+        trpl.pvSim(pl, None, None, None, truth[None, :12], simPar, inis[c], (128,), 0, 1, init_mode="points")
+        ts.append(grid.copy()); vs.append(np.log10(pl[0])); us.append(np.full(T + 1, 0.1))
+    prob = trpl.engine.Problem(simPar, inis, [(ts, vs, us)], device=0)
+    X = prior_samples(6, seed=77)
+    X[0] = truth
+    X[1] = truth; X[1, 12] = 0.25            # same curves, shifted by mag_offset
+    X[3] = X[2]
+    lnl, status, _ = trpl.engine.solve_loglik(torch.from_numpy(X).cuda(), prob)
+    got = lnl.cpu().numpy()[0]
+    assert (status.cpu().numpy() == 0).all()
+    assert (got <= 0).all()
+    assert abs(got[0]) < 1e-12
+    np.testing.assert_allclose(got[1], -3 * (T + 1) * 0.25 ** 2, rtol=1e-9)
+    assert got[2] == got[3]
+    assert got[2] < got[0]
