@@ -102,13 +102,122 @@ __device__ __forceinline__ double warp_sum(double v)
 
 __device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
 
-// Tridiagonal solve, M rows per lane (row n = M*lane + j):  l[j] x[n-1] + d[j] x[n] + u[j] x[n+1] = b[j].
+// ---------------------------------------------------------------------------------------------
+// Communication among the lanes that share one simulation.  W = warps per simulation.
+//   W == 1: warp shuffles / votes only (the production path for L <= 256).
+//   W  > 1: one CTA of W warps per simulation (fine grids, L up to 128*W); values travel through a
+//           ping-pong exchange buffer in shared memory, one __syncthreads per exchange.  Every
+//           thread of the CTA executes the same sequence of exchanges.
+// g = index of this lane among the 32*W lanes of the simulation.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+struct Comm {
+    int g;            // lane index within the simulation
+    double *xb;       // W > 1: exchange buffer [2][3][G] doubles
+    double *red;      // W > 1: reduction scratch [2][W][4] doubles
+    int phase;        // ping-pong selector of xb
+    int rphase;       // ping-pong selector of red
+
+    // K values from lane g-dm (-> vm) and lane g+dp (-> vp); out-of-range sources return the
+    // caller's own value (always multiplied by an exact zero downstream).
+    template <int K, bool WANT_M, bool WANT_P>
+    __device__ __forceinline__ void xchg(const double (&v)[K], const int dm, const int dp,
+                                         double (&vm)[K], double (&vp)[K])
+    {
+        if constexpr (W == 1) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (WANT_M) vm[k] = __shfl_up_sync(FULL, v[k], dm);
+                if (WANT_P) vp[k] = __shfl_down_sync(FULL, v[k], dp);
+            }
+        } else {
+            constexpr int G = 32 * W;
+            double *buf = xb + phase * (3 * G);
+#pragma unroll
+            for (int k = 0; k < K; k++) buf[k * G + g] = v[k];
+            __syncthreads();
+            const int im = (g - dm >= 0) ? g - dm : g;
+            const int ip = (g + dp < G) ? g + dp : g;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (WANT_M) vm[k] = buf[k * G + im];
+                if (WANT_P) vp[k] = buf[k * G + ip];
+            }
+            phase ^= 1;
+        }
+    }
+    __device__ __forceinline__ double from_prev(const double v)     // value of lane g-1
+    {
+        double a[1] = {v}, m[1], p_[1];
+        xchg<1, true, false>(a, 1, 1, m, p_);
+        return m[0];
+    }
+    __device__ __forceinline__ double from_next(const double v)     // value of lane g+1
+    {
+        double a[1] = {v}, m[1], p_[1];
+        xchg<1, false, true>(a, 1, 1, m, p_);
+        return p_[0];
+    }
+    __device__ __forceinline__ bool all(const bool pred)
+    {
+        if constexpr (W == 1) return __all_sync(FULL, pred);
+        else return __syncthreads_and(pred) != 0;
+    }
+    __device__ __forceinline__ double sum(double v)                 // total over the simulation
+    {
+        v = warp_sum(v);
+        if constexpr (W > 1) {
+            double *r = red + rphase * (W * 4);
+            if ((threadIdx.x & 31) == 0) r[(threadIdx.x >> 5) * 4] = v;
+            __syncthreads();
+            v = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; w++) v += r[w * 4];
+            rphase ^= 1;
+        }
+        return v;
+    }
+    // stop rule: errN = rN/sbN < TOL and errP = rP/sbP < TOL  (pvSimPCR.py:213-216)
+    __device__ __forceinline__ void stop_rule(const double rN, const double sbN, const double rP,
+                                              const double sbP, const double TOL, bool &converged,
+                                              bool &nonfinite)
+    {
+        const int lane = threadIdx.x & 31;
+        const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+        double k0 = hi16 ? sbN : rN, k1 = hi16 ? sbP : rP;
+        const double s0 = hi16 ? rN : sbN, s1 = hi16 ? rP : sbP;
+        k0 += __shfl_xor_sync(FULL, s0, 16);
+        k1 += __shfl_xor_sync(FULL, s1, 16);
+        double k = hi8 ? k1 : k0;
+        const double sd = hi8 ? k0 : k1;
+        k += __shfl_xor_sync(FULL, sd, 8);
+        k += __shfl_xor_sync(FULL, k, 4);
+        k += __shfl_xor_sync(FULL, k, 2);
+        k += __shfl_xor_sync(FULL, k, 1);
+        // lanes 0-7: sum rN, 8-15: sum rP, 16-23: sum |bN|, 24-31: sum |bP|  (of this warp)
+        if constexpr (W > 1) {
+            double *r = red + rphase * (W * 4);
+            if ((lane & 7) == 0) r[(threadIdx.x >> 5) * 4 + (lane >> 3)] = k;
+            __syncthreads();
+            k = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; w++) k += r[w * 4 + (lane >> 3)];
+            rphase ^= 1;
+        }
+        const double other = __shfl_xor_sync(FULL, k, 16);
+        const double err = k * rcp64(other);                       // lanes 0-7: errN, 8-15: errP
+        converged = (__ballot_sync(FULL, err < TOL) & 0xffffu) == 0xffffu;
+        nonfinite = (__ballot_sync(FULL, !(fabs(err) <= DBL_MAX)) & 0xffffu) != 0u;
+    }
+};
+
+// Tridiagonal solve, M rows per lane (row n = M*g + j):  l[j] x[n-1] + d[j] x[n] + u[j] x[n+1] = b[j].
 // Rows outside the physical system must be identity rows (l=u=0, d=1).  l of the first row
 // and u of the last physical row must be 0.
-template <int M>
+template <int M, int W>
 __device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double (&d)[M],
                                               const double (&u)[M], const double (&b)[M],
-                                              double (&x)[M])
+                                              double (&x)[M], Comm<W> &cm)
 {
     double Lr, Dr, Ur, Br;
     double c[M > 1 ? M - 1 : 1], y[M > 1 ? M - 1 : 1], v[M > 1 ? M - 1 : 1], w[M > 1 ? M - 1 : 1];
@@ -145,9 +254,9 @@ __device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double
             w[j] = -c[j] * w[j + 1];
         }
         // interface row (local M-1) couples s_left, s_own and the next lane's first interior row
-        const double y0n = __shfl_down_sync(FULL, y[0], 1);
-        const double v0n = __shfl_down_sync(FULL, v[0], 1);
-        const double w0n = __shfl_down_sync(FULL, w[0], 1);
+        double mine[3] = {y[0], v[0], w[0]}, nm[3], nx[3];
+        cm.template xchg<3, false, true>(mine, 1, 1, nm, nx);
+        const double y0n = nx[0], v0n = nx[1], w0n = nx[2];
         const double lr = l[M - 1], ur = u[M - 1];
         Lr = -lr * v[M - 2];
         Dr = fma(-ur, v0n, fma(-lr, w[M - 2], d[M - 1]));
@@ -156,25 +265,23 @@ __device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double
     } else {
         Lr = l[0]; Dr = d[0]; Ur = u[0]; Br = b[0];
     }
-    // 32-lane parallel cyclic reduction with unit diagonal
+    // parallel cyclic reduction over the 32*W interface unknowns, unit diagonal
     {
         double inv = rcp64(Dr);
         Lr *= inv; Ur *= inv; Br *= inv;
     }
 #pragma unroll
-    for (int rf = 1; rf < 32; rf <<= 1) {
-        // Off-diagonals shrink quadratically per stage; once every |L|,|U| of the warp is below
-        // 2^-70 the remaining stages cannot change D = 1 or B in the last bit: stop (warp-uniform).
+    for (int rf = 1; rf < 32 * W; rf <<= 1) {
+        // Off-diagonals shrink quadratically per stage; once every |L|,|U| of the simulation is
+        // below 2^-70 the remaining stages cannot change D = 1 or B in the last bit: stop.
         if (rf >= 2) {
             const int hl = __double2hiint(Lr) & 0x7fffffff, hu = __double2hiint(Ur) & 0x7fffffff;
-            if (__all_sync(FULL, max(hl, hu) < ((1023 - 70) << 20))) break;
+            if (cm.all(max(hl, hu) < ((1023 - 70) << 20))) break;
         }
-        const double Lm = __shfl_up_sync(FULL, Lr, rf);
-        const double Um = __shfl_up_sync(FULL, Ur, rf);
-        const double Bm = __shfl_up_sync(FULL, Br, rf);
-        const double Lp = __shfl_down_sync(FULL, Lr, rf);
-        const double Up = __shfl_down_sync(FULL, Ur, rf);
-        const double Bp = __shfl_down_sync(FULL, Br, rf);
+        double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
+        cm.template xchg<3, true, true>(mine, rf, rf, vm, vp);
+        const double Lm = vm[0], Um = vm[1], Bm = vm[2];
+        const double Lp = vp[0], Up = vp[1], Bp = vp[2];
         const double D = fma(-Lp, Ur, fma(-Um, Lr, 1.0));
         const double B = fma(-Bp, Ur, fma(-Bm, Lr, Br));
         const double Ln = -Lm * Lr;
@@ -186,7 +293,7 @@ __device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double
     }
     x[M - 1] = Br;
     if constexpr (M > 1) {
-        const double sl = __shfl_up_sync(FULL, Br, 1);
+        const double sl = cm.from_prev(Br);
 #pragma unroll
         for (int j = 0; j < M - 1; j++) x[j] = fma(-w[j], Br, fma(-v[j], sl, y[j]));
     }
@@ -230,12 +337,16 @@ struct WarpScratch {      // per-warp shared scratch touched once every 32 PL sa
 };
 
 // ---------------------------------------------------------------------------------------------
-// one (sample, curve) simulation, executed by one warp
+// one (sample, curve) simulation, executed by W warps (W == 1: one warp; W > 1: one CTA)
 // ---------------------------------------------------------------------------------------------
-template <int M, bool PAD>
+template <int M, bool PAD, int W>
 __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long long s,
-                                        double *ring_warp, WarpScratch *ws, const int lane)
+                                        double *ring_warp, WarpScratch *ws, const int lane,
+                                        Comm<W> &cm)
 {
+    constexpr int G = 32 * W;
+    const int g = cm.g;                         // lane index within the simulation
+    const bool io_warp = (W == 1) || (g < 32);  // the warp that stages, stores and scores PL
     const CurveDev &cv = a.curves[c];
     const int L = a.L;
     const int flags = a.flags;
@@ -260,26 +371,26 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
 
     // ---- geometry of this lane
     const int last_lane = (L - 1) / M;         // lane owning node L-1 (at j = M-1 since L % M == 0)
-    bool ev[M + 1];                            // edge m = M*lane + j is an interior edge (1..L-1)
+    bool ev[M + 1];                            // edge m = M*g + j is an interior edge (1..L-1)
 #pragma unroll
     for (int j = 0; j <= M; j++) {
-        const int m = M * lane + j;
-        // exact-fit grids (L == 32*M): only edge 0 (lane 0) and edge L (lane 31) are boundaries,
-        // so the selects on the inner edges fold away at compile time
-        ev[j] = PAD ? ((m >= 1) && (m <= L - 1)) : (j == 0 ? (lane != 0) : (j == M ? (lane != 31) : true));
+        const int m = M * g + j;
+        // exact-fit grids (L == M*G): only edge 0 (first lane) and edge L (last lane) are
+        // boundaries, so the selects on the inner edges fold away at compile time
+        ev[j] = PAD ? ((m >= 1) && (m <= L - 1)) : (j == 0 ? (g != 0) : (j == M ? (g != G - 1) : true));
     }
-    bool nv[M];                                // node n = M*lane + j exists
+    bool nv[M];                                // node n = M*g + j exists
 #pragma unroll
-    for (int j = 0; j < M; j++) nv[j] = PAD ? (M * lane + j < L) : true;
+    for (int j = 0; j < M; j++) nv[j] = PAD ? (M * g + j < L) : true;
     // surface rows: lane 0 applies the front surface to j=0, last_lane the back surface to j=M-1
-    const bool is_first = (lane == 0), is_last = (lane == last_lane);
+    const bool is_first = (g == 0), is_last = (g == last_lane);
     const double srf = is_first ? sr0 : (is_last ? srL : 0.0);
 
     // ---- initial state (pvSimPCR.py:339-362): N = N0 + dN, P = P0 + dN, E = 0
     double N[M], P[M], E[M];
 #pragma unroll
     for (int j = 0; j < M; j++) {
-        const int n = M * lane + j;
+        const int n = M * g + j;
         double dn = 0.0;
         if (n < L) dn = cv.init[n] * cv.init_mul;
         N[j] = nv[j] ? N0 + dn : 0.0;
@@ -297,16 +408,23 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
 #pragma unroll
             for (int f = 0; f < 3; f++) ring.store(sl, f, z);
     }
-    if (lane < TRPL_MAX_EXP) {
+    if (io_warp && lane < TRPL_MAX_EXP) {
         ws->sse[lane] = 0.0;
         ws->pos[lane] = 0;
     }
     __syncwarp();
 
     // neighbour values carried across iterations and steps
-    double Nl = __shfl_up_sync(FULL, N[M - 1], 1), Nr = __shfl_down_sync(FULL, N[0], 1);
-    double Pl = __shfl_up_sync(FULL, P[M - 1], 1), Pr = __shfl_down_sync(FULL, P[0], 1);
-    double En = 0.0;   // E on edge M*lane + M (owned by the next lane)
+    double Nl, Nr, Pl, Pr;
+    {
+        double mine[2] = {N[M - 1], P[M - 1]}, vm[2], vp[2];
+        cm.template xchg<2, true, false>(mine, 1, 1, vm, vp);
+        Nl = vm[0]; Pl = vm[1];
+        double mine2[2] = {N[0], P[0]};
+        cm.template xchg<2, false, true>(mine2, 1, 1, vm, vp);
+        Nr = vp[0]; Pr = vp[1];
+    }
+    double En = 0.0;   // E on edge M*g + M (owned by the next lane)
 
     const double mLN0P0 = -(double)L * N0P0;   // pvSimPCR.py:278
     const int t_last = cv.t_last;
@@ -401,7 +519,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             double part = 0.0;
 #pragma unroll
             for (int j = 0; j < M; j++) part = fma(N[j], P[j], part);
-            const double tot = warp_sum(part);
+            const double tot = cm.sum(part);
             const double plraw = rate * (tot + mLN0P0);
             if (lane == (pl_idx & 31)) keep = plraw;
             t_next_pl += plT;
@@ -517,9 +635,9 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     rN += fabs(res);
                     sbN += fabs(b[j]);
                 }
-                tridiag_solve<M>(l, d, u, b, N);
-                Nl = __shfl_up_sync(FULL, N[M - 1], 1);
-                Nr = __shfl_down_sync(FULL, N[0], 1);
+                tridiag_solve<M, W>(l, d, u, b, N, cm);
+                Nl = cm.from_prev(N[M - 1]);
+                Nr = cm.from_next(N[0]);
             }
 
             // ======== P system (new N) ========
@@ -579,27 +697,11 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 }
                 // ---- stop decision for THIS iteration (pvSimPCR.py:213-216): both L1 residuals are
                 // known here, before the P solve; reducing them now lets the shuffle chain overlap
-                // the solve.  Lanes 0-7 end up with errN, lanes 8-15 with errP.
-                {
-                    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
-                    double k0 = hi16 ? sbN : rN, k1 = hi16 ? sbP : rP;
-                    const double s0 = hi16 ? rN : sbN, s1 = hi16 ? rP : sbP;
-                    k0 += __shfl_xor_sync(FULL, s0, 16);
-                    k1 += __shfl_xor_sync(FULL, s1, 16);
-                    double k = hi8 ? k1 : k0;
-                    const double sd = hi8 ? k0 : k1;
-                    k += __shfl_xor_sync(FULL, sd, 8);
-                    k += __shfl_xor_sync(FULL, k, 4);
-                    k += __shfl_xor_sync(FULL, k, 2);
-                    k += __shfl_xor_sync(FULL, k, 1);
-                    const double other = __shfl_xor_sync(FULL, k, 16);
-                    const double err = k * rcp64(other);
-                    converged_now = (__ballot_sync(FULL, err < TOL) & 0xffffu) == 0xffffu;
-                    nonfinite_now = (__ballot_sync(FULL, !(fabs(err) <= DBL_MAX)) & 0xffffu) != 0u;
-                }
-                tridiag_solve<M>(l, d, u, b, P);
-                Pl = __shfl_up_sync(FULL, P[M - 1], 1);
-                Pr = __shfl_down_sync(FULL, P[0], 1);
+                // the solve.
+                cm.stop_rule(rN, sbN, rP, sbP, TOL, converged_now, nonfinite_now);
+                tridiag_solve<M, W>(l, d, u, b, P, cm);
+                Pl = cm.from_prev(P[M - 1]);
+                Pr = cm.from_next(P[0]);
             }
 
             // ======== E update on interior edges                           (pvSimPCR.py:205-209)
@@ -611,7 +713,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 const double num = fma(LamDP, P[j] - Pm, fma(-LamDN, N[j] - Nm, -bE[j]));
                 E[j] = sel(ev[j], num * rcp64(den), 0.0);
             }
-            En = __shfl_down_sync(FULL, E[0], 1);
+            En = cm.from_next(E[0]);
 
             // ======== stop rule (pvSimPCR.py:213-216): decided by the flags computed before the P solve
             it++;
@@ -627,12 +729,12 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             if (emitted) pl_idx--;
             break;
         }
-        if (emitted && (pl_idx & 31) == 0) flush(pl_idx - 32, 32);
+        if (io_warp && emitted && (pl_idx & 31) == 0) flush(pl_idx - 32, 32);
     }
 
     // ---- tail: partially filled block; after a failure everything from pl_idx on is NaN
-    if (pl_idx & 31) flush(pl_idx & ~31, pl_idx & 31);
-    if (failed && cv.pl_out != nullptr) {
+    if (io_warp && (pl_idx & 31)) flush(pl_idx & ~31, pl_idx & 31);
+    if (io_warp && failed && cv.pl_out != nullptr) {
         const double qnan = __longlong_as_double(0x7ff8000000000000LL);
         for (int i = pl_idx + lane; i < n_pl; i += 32) {
             if (a.pl_dtype == TRPL_F32)
@@ -644,12 +746,12 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
 
     // ---- results
     __syncwarp();
-    if (lane == 0) {
+    if (io_warp && lane == 0) {
         const long long cs = (long long)c * a.S + s;
         if (a.status) a.status[cs] = status;
         if (a.iters) a.iters[cs] = iters_total;
     }
-    if (a.sse != nullptr && lane < a.E) {
+    if (io_warp && a.sse != nullptr && lane < a.E) {
         double v = ws->sse[lane];
         if (failed && ws->pos[lane] < cv.obs[lane].n) v = __longlong_as_double(0x7ff8000000000000LL);
         a.sse[((long long)lane * a.C + c) * a.S + s] = v;
@@ -666,6 +768,8 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32);
     const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
+    Comm<1> cm;
+    cm.g = lane; cm.xb = nullptr; cm.red = nullptr; cm.phase = 0; cm.rphase = 0;
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(a.counter, 1ULL);
@@ -673,7 +777,36 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
         if (item >= total) break;
         const long long s = (long long)(item / (unsigned)a.C);
         const int c = (int)(item % (unsigned)a.C);
-        run_sim<M, PAD>(a, c, s, ring_warp, &scratch[warp], lane);
+        run_sim<M, PAD, 1>(a, c, s, ring_warp, &scratch[warp], lane, cm);
+    }
+}
+
+// Fine grids: one CTA of W warps per simulation, 4 nodes per lane (L <= 128*W).
+template <int W>
+__global__ void __launch_bounds__(W * 32, 16 / W)
+trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
+{
+    constexpr int M = 4;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ WarpScratch scratch;
+    __shared__ unsigned long long next_item;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32);
+    Comm<W> cm;
+    cm.g = threadIdx.x;
+    cm.xb = smem + (size_t)W * (4 * 3 * M * 32);
+    cm.red = cm.xb + 2 * 3 * 32 * W;
+    cm.phase = 0; cm.rphase = 0;
+    const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_item = atomicAdd(a.counter, 1ULL);
+        __syncthreads();
+        const unsigned long long item = next_item;
+        if (item >= total) break;
+        const long long s = (long long)(item / (unsigned)a.C);
+        const int c = (int)(item % (unsigned)a.C);
+        run_sim<M, true, W>(a, c, s, ring_warp, &scratch, lane, cm);
     }
 }
 
@@ -836,22 +969,38 @@ void make_scales(double length, double time, int L, int T, double *sc, double *d
     *dx_o = dx; *dt_o = dt;
 }
 
-struct Cfg { int M; bool pad; };
+struct Cfg { int M; bool pad; int W; };      // W = warps per simulation (1: warp kernel, >1: CTA kernel)
 int pick_cfg(int L, Cfg *cfg)
 {
     if (L < 2) return TRPL_EINVAL;
-    int M = 1;
-    while (M <= 8 && 32 * M < L) M <<= 1;
-    if (M > 8) return TRPL_EUNSUPPORTED;          // L > 256: multi-warp simulations not built yet
-    if (L % M != 0 || L < 2 * M) return TRPL_EUNSUPPORTED;
-    cfg->M = M;
-    cfg->pad = (L != 32 * M);
+    if (L <= 256) {
+        int M = 1;
+        while (32 * M < L) M <<= 1;
+        if (L % M == 0 && L >= 2 * M) {
+            cfg->M = M; cfg->pad = (L != 32 * M); cfg->W = 1;
+            return TRPL_OK;
+        }
+        if (L < 128) return TRPL_EUNSUPPORTED;    // odd small grids: need L % M == 0
+    }
+    // fine grids: 4 nodes per lane, W warps per simulation
+    if (L % 4 != 0 || L > 128 * 16) return TRPL_EUNSUPPORTED;
+    int W = 2;
+    while (128 * W < L) W <<= 1;
+    cfg->M = 4; cfg->pad = true; cfg->W = W;
     return TRPL_OK;
 }
 
 typedef void (*kern_t)(const KArgs);
 kern_t pick_kernel(const Cfg &c)
 {
+    if (c.W > 1) {
+        switch (c.W) {
+        case 2: return trpl_sim_cta_kernel<2>;
+        case 4: return trpl_sim_cta_kernel<4>;
+        case 8: return trpl_sim_cta_kernel<8>;
+        default: return trpl_sim_cta_kernel<16>;
+        }
+    }
     switch (c.M) {
     case 1: return c.pad ? trpl_sim_kernel<1, true> : trpl_sim_kernel<1, false>;
     case 2: return c.pad ? trpl_sim_kernel<2, true> : trpl_sim_kernel<2, false>;
@@ -860,15 +1009,31 @@ kern_t pick_kernel(const Cfg &c)
     }
 }
 
+// threads per CTA, simulations per CTA and dynamic shared memory of a configuration
+void cfg_shape(const Cfg &c, int *threads, int *sims_per_cta, size_t *smem)
+{
+    const size_t ring = (size_t)4 * 3 * c.M * 32 * sizeof(double);       // per warp
+    if (c.W > 1) {
+        *threads = c.W * 32;
+        *sims_per_cta = 1;
+        *smem = c.W * ring + (size_t)(2 * 3 * 32 * c.W + 2 * c.W * 4) * sizeof(double);
+    } else {
+        *threads = WARPS_PER_CTA * 32;
+        *sims_per_cta = WARPS_PER_CTA;
+        *smem = WARPS_PER_CTA * ring;
+    }
+}
+
 int kernel_geometry(int device, const Cfg &cfg, kern_t *k_out, size_t *smem_out, int *ctas_per_sm,
                     int *sms)
 {
     kern_t k = pick_kernel(cfg);
-    const size_t smem = (size_t)WARPS_PER_CTA * 4 * 3 * cfg.M * 32 * sizeof(double);
+    int threads, spc; size_t smem;
+    cfg_shape(cfg, &threads, &spc, &smem);
     CK(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k, WARPS_PER_CTA * 32, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k, threads, smem));
     if (nb < 1) return TRPL_EUNSUPPORTED;
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
@@ -896,12 +1061,14 @@ int launch_sims(KArgs &ka, const Cfg &cfg, int device, cudaStream_t st)
     CK(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     ka.counter = counter;
+    int threads, spc; size_t smem2;
+    cfg_shape(cfg, &threads, &spc, &smem2);
     const unsigned long long items = (unsigned long long)ka.S * ka.C;
-    unsigned long long want = (items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    unsigned long long want = (items + spc - 1) / spc;
     unsigned long long cap = (unsigned long long)nb * nsm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     if (grid > 0) {
-        k<<<grid, WARPS_PER_CTA * 32, smem, st>>>(ka);
+        k<<<grid, threads, smem, st>>>(ka);
         CK(cudaGetLastError());
     }
     CK(cudaFreeAsync(counter, st));
@@ -922,8 +1089,9 @@ const char *trpl_error_string(int code)
     switch (code) {
     case TRPL_OK: return "ok";
     case TRPL_EINVAL: return "invalid argument";
-    case TRPL_EUNSUPPORTED: return "unsupported shape (need L = M*g, M in {1,2,4,8}, 2 <= g <= 32; "
-                                   "curves <= 8, observation files <= 4)";
+    case TRPL_EUNSUPPORTED: return "unsupported shape (need L <= 256 with L = M*g, M in {1,2,4,8}, "
+                                   "2 <= g <= 32, or L <= 2048 with L % 4 == 0; curves <= 8, "
+                                   "observation files <= 4)";
     case TRPL_ECUDA: return "CUDA runtime error";
     case TRPL_ENODEVICE: return "no usable CUDA device";
     default: return "unknown error";
@@ -942,7 +1110,9 @@ int trpl_resident_sims(int device, int L)
     kern_t k; size_t smem; int nb, nsm;
     rc = kernel_geometry(device, cfg, &k, &smem, &nb, &nsm);
     if (rc) return rc;
-    return nb * nsm * WARPS_PER_CTA;
+    int threads, spc; size_t smem2;
+    cfg_shape(cfg, &threads, &spc, &smem2);
+    return nb * nsm * spc;
 }
 
 int trpl_solve_pl(const double *d_matpar, int64_t S, int64_t ld_matpar, const double *d_init,

@@ -377,3 +377,42 @@ def test_likelihood_properties_at_full_size(trpl):
     np.testing.assert_allclose(got[1], -3 * (T + 1) * 0.25 ** 2, rtol=1e-9)
     assert got[2] == got[3]
     assert got[2] < got[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# fine grids: one CTA of W warps per simulation (BASELINE config 5 shape: L = 1000)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,T", [(1000, 250), (512, 300), (1024, 120), (2048, 60), (260, 300)])
+def test_fine_grid_cta_kernel_matches_oracle(trpl, oracle, L, T):
+    length = 2000.0
+    simPar = [length, 0.025 * T, L, T, 1, (0,), 7, 10000]
+    X = prior_samples(5, seed=L + 1)
+    X[0] = TRUTH * UC
+    x = (np.arange(L) + 0.5) * (length / L)
+    for amp in (1.2738e16, 1.6485e18):
+        ini = amp * 1e-21 * np.exp(-6e-3 * x)
+        ref = oracle.solve(X[:, :12], simPar, ini, solver="pcr" if (L & (L - 1)) == 0 else "thomas")
+        pl = np.empty((len(X), T + 1))
+        st = np.zeros(len(X), dtype=np.int32)
+        trpl.pvSim(pl, None, None, None, X[:, :12], simPar, ini, (128,), 0, 1, init_mode="points",
+                   status_out=st)
+        assert (st == 0).all() and (ref["status"] == 0).all()
+        _assert_pl_close(pl, ref["pl"], X[:, :12], simPar)
+
+
+def test_fine_grid_fused_likelihood(trpl, oracle):
+    """Config 5 shape at reduced size: L=1000, 3 curves dN_c(x) = A_c exp(-6e-3 x)."""
+    L, T, length = 1000, 160, 2000.0
+    simPar = [length, 0.025 * T, L, T, 1, (0,), 7, 10000]
+    x = (np.arange(L) + 0.5) * (length / L)
+    inis = np.stack([a * 1e-21 * np.exp(-6e-3 * x) for a in (1.2738e16, 1.1539e17, 1.6485e18)])
+    rng = np.random.default_rng(2)
+    e_data = _synthetic_edata(oracle, simPar, inis, [length] * 3, rng, n_exp=1, every=(1, 2, 4))
+    X = prior_samples(7, seed=1000, mag=True)
+    X[0] = TRUTH * UC
+    ref = oracle.loglik(X, simPar, inis, e_data, solver="thomas")
+    prob = trpl.engine.Problem(simPar, inis, e_data, device=0)
+    lnl, status, _ = trpl.engine.solve_loglik(torch.from_numpy(X).cuda(), prob)
+    torch.cuda.synchronize()
+    assert (status.cpu().numpy() == 0).all()
+    np.testing.assert_allclose(lnl.cpu().numpy(), ref, rtol=1e-6, atol=1e-9)
