@@ -99,7 +99,7 @@ def init_points(iniPar, length, L, init_mode="points"):
 
 
 def solve(matPar, simPar, iniPar, init_mode="points", solver="pcr", max_order=5, nthreads=0,
-          return_state=False, raw=False):
+          return_state=False, raw=False, simulator_pow=False):
     """Oracle of pvSimPCR.pvSim (pvSimPCR.py:309-401) for ONE curve.
 
     matPar [S,12] physical units; simPar = [Length, Time, L, T, plT, pT, tol, MAX].
@@ -108,7 +108,7 @@ def solve(matPar, simPar, iniPar, init_mode="points", solver="pcr", max_order=5,
     Length, Time, L, T, plT, _pT, tol, MAX = simPar
     mp = np.ascontiguousarray(np.asarray(matPar, dtype=np.float64)[:, :12])
     S = mp.shape[0]
-    flags = 2 if raw else 0
+    flags = (2 if raw else 0) | (4 if simulator_pow else 0)
     if init_mode == "exp":
         # The reference scales a by dx^3 and evaluates the profile in grid units
         # (pvSimPCR.py:347-353); pass it through unscaled (flag bit0).
