@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Short fused-likelihood launch for ncu / quick timing: power-scan shape with a reduced number
-of time steps (same kernel, same per-step work).  usage: profile_case.py [T] [S] [reps]"""
+of time steps (same kernel, same per-step work).  usage: profile_case.py [T] [S] [reps] [L]"""
 import os
 import sys
 import time
@@ -17,9 +17,13 @@ from helpers import TRUTH, UC, power_scan_excitations, prior_samples  # noqa: E4
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-L = 128
+L = int(sys.argv[4]) if len(sys.argv) > 4 else 128
 simPar = [2000.0, 0.025 * T, L, T, 1, (0,), 7, 10000]
-inis = power_scan_excitations()
+if L == 128:
+    inis = power_scan_excitations()
+else:   # BASELINE config 5: dN_c(x) = A_c exp(-6e-3 x) at the cell centres
+    xc = (np.arange(L) + 0.5) * (2000.0 / L)
+    inis = np.stack([a * 1e-21 * np.exp(-6e-3 * xc) for a in (1.2738e16, 1.1539e17, 1.6485e18)])
 res = trpl.engine.resident_sims(L, 0)
 if S <= 0:
     S = res
