@@ -91,6 +91,15 @@ def lib():
     L.trpl_obs_prepare.argtypes = [vp, ctypes.c_int32, dbl, i32, vp, vp, vp]
     L.trpl_lse_partial.restype = i32
     L.trpl_lse_partial.argtypes = [vp, i64, vp, i32, vp]
+    u64 = ctypes.c_uint64
+    L.trpl_random_grid.restype = i32
+    L.trpl_random_grid.argtypes = [vp, i64, i64, vp, vp, vp, i32, i32, u64, u64, i32, vp]
+    L.trpl_posterior_weights.restype = i32
+    L.trpl_posterior_weights.argtypes = [vp, i64, dbl, vp, i32, vp]
+    L.trpl_weighted_hist.restype = i32
+    L.trpl_weighted_hist.argtypes = [vp, i64, i64, i32, i32, vp, dbl, dbl, i32, dbl, dbl, i32, vp, i32, vp]
+    L.trpl_weighted_moments.restype = i32
+    L.trpl_weighted_moments.argtypes = [vp, i64, i64, i32, vp, vp, i32, vp]
     L.trpl_bench_dfma.restype = i32
     L.trpl_bench_dfma.argtypes = [i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     _lib = L
@@ -99,7 +108,8 @@ def lib():
 
 EXPORTS = ["trpl_version", "trpl_error_string", "trpl_last_cuda_error", "trpl_resident_sims",
            "trpl_solve_pl", "trpl_solve_loglik", "trpl_log10_clamp", "trpl_lnp_accumulate",
-           "trpl_obs_prepare", "trpl_lse_partial", "trpl_bench_dfma"]
+           "trpl_obs_prepare", "trpl_lse_partial", "trpl_bench_dfma", "trpl_random_grid",
+           "trpl_posterior_weights", "trpl_weighted_hist", "trpl_weighted_moments"]
 
 
 def check(rc, what):

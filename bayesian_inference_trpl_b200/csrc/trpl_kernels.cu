@@ -924,6 +924,136 @@ __global__ void trpl_lse_init_kernel(double *out)
     out[1] = 0.0;
 }
 
+// ---- sample generation on the device (bayeslib.random_grid / make_grid, bayeslib.py:18-76) -----
+// Counter-based Philox4x32-10: sample s, column j uses counter (s_lo, s_hi, j, 0) and key (seed_lo,
+// seed_hi); u = 53 random bits / 2^53.  Same bounds / log / override semantics as the reference.
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                              unsigned k0, unsigned k1, unsigned (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct GridArgs {
+    double lo[16], hi[16];
+    int do_log[16];
+    int ncol, eq_mu, eq_s, eq_auger;
+};
+
+__global__ void trpl_random_grid_kernel(double *x, long long S, long long ldx, const GridArgs ga,
+                                        unsigned long long seed, unsigned long long first)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long total = S * ga.ncol;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long s = i / ga.ncol;
+        const int j = (int)(i - s * ga.ncol);
+        int src = j;                                   // override_equal_*: copy the draw of another column
+        if (ga.eq_mu && j == 2) src = 3;
+        if (ga.eq_s && j == 6) src = 5;
+        if (ga.eq_auger && j == 8) src = 7;
+        const unsigned long long id = first + (unsigned long long)s;
+        unsigned r[4];
+        philox4x32_10((unsigned)id, (unsigned)(id >> 32), (unsigned)src, 0u, (unsigned)seed,
+                      (unsigned)(seed >> 32), r);
+        const unsigned long long bits = (((unsigned long long)r[0] << 32) | r[1]) >> 11;
+        const double u = (double)bits * (1.0 / 9007199254740992.0);
+        const double lo = ga.lo[src], hi = ga.hi[src];
+        double v;
+        if (lo == hi) v = lo;
+        else if (ga.do_log[src]) {
+            const double a = log10(lo), b = log10(hi);
+            v = exp10(a + (b - a) * u);
+        } else v = lo + (hi - lo) * u;
+        x[s * ldx + j] = v;
+    }
+}
+
+// ---- posterior products (Visualization/utils.py:157-285) -------------------------------------
+__global__ void trpl_weights_kernel(const double *lnp, long long n, double lse, double *w)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = lnp[i];
+        w[i] = (v == v) ? exp(v - lse) : 0.0;
+    }
+}
+
+// numpy.histogram bin of v over nb uniform bins on [lo, hi] (right edge inclusive), or -1
+__device__ __forceinline__ int hist_bin(double v, double lo, double hi, int nb)
+{
+    if (!(v >= lo) || !(v <= hi)) return -1;
+    int b = (int)((v - lo) / (hi - lo) * nb);
+    if (b >= nb) b = nb - 1;
+    // guard the edges against rounding of the scaled position (numpy does the same correction)
+    const double e0 = lo + (hi - lo) * b / nb, e1 = lo + (hi - lo) * (b + 1) / nb;
+    if (v < e0 && b > 0) b--;
+    else if (v >= e1 && b < nb - 1) b++;
+    return b;
+}
+
+__global__ void trpl_hist_kernel(const double *x, long long ldx, int colx, int coly, const double *w,
+                                 long long n, double lox, double hix, int nbx, double loy, double hiy,
+                                 int nby, double *hist)
+{
+    extern __shared__ double sh[];
+    const int nb = nbx * (coly >= 0 ? nby : 1);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int bx = hist_bin(x[i * ldx + colx], lox, hix, nbx);
+        int b = bx;
+        if (coly >= 0) {
+            const int by = hist_bin(x[i * ldx + coly], loy, hiy, nby);
+            b = (bx < 0 || by < 0) ? -1 : bx * nby + by;
+        }
+        if (b >= 0) atomicAdd(&sh[b], w ? w[i] : 1.0);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (sh[i] != 0.0) atomicAdd(&hist[i], sh[i]);
+}
+
+// out[0] = sum w, out[1+j] = sum w x_j, out[1+ncol+j*ncol+k] = sum w x_j x_k
+__global__ void trpl_moments_kernel(const double *x, long long ldx, int ncol, const double *w,
+                                    long long n, double *out)
+{
+    constexpr int TILE = 64;
+    __shared__ double tx[TILE][17];
+    __shared__ double tw[TILE];
+    const int nacc = 1 + ncol + ncol * ncol;
+    const int a = threadIdx.x;
+    int j = -1, k = -1;
+    if (a >= 1 && a < 1 + ncol) j = a - 1;
+    else if (a >= 1 + ncol && a < nacc) { j = (a - 1 - ncol) / ncol; k = (a - 1 - ncol) % ncol; }
+    double acc = 0.0;
+    for (long long base = (long long)blockIdx.x * TILE; base < n; base += (long long)gridDim.x * TILE) {
+        const int rows = (int)((n - base < TILE) ? (n - base) : TILE);
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * ncol; i += blockDim.x)
+            tx[i / ncol][i % ncol] = x[(base + i / ncol) * ldx + (i % ncol)];
+        for (int i = threadIdx.x; i < rows; i += blockDim.x) tw[i] = w[base + i];
+        __syncthreads();
+        if (a < nacc) {
+            for (int r = 0; r < rows; r++) {
+                const double ww = tw[r];
+                if (a == 0) acc += ww;
+                else if (k < 0) acc = fma(ww, tx[r][j], acc);
+                else acc = fma(ww * tx[r][j], tx[r][k], acc);
+            }
+        }
+    }
+    if (a < nacc && acc != 0.0) atomicAdd(&out[a], acc);
+}
+
 // ---- FP64 FMA pipe microbenchmark ------------------------------------------------------------
 __global__ void trpl_dfma_kernel(double *out, int iters, double seed)
 {
@@ -1296,6 +1426,92 @@ int trpl_lse_partial(const double *d_x, int64_t n, double *d_out2, int device, v
         trpl_lse_max_kernel<<<(unsigned)blocks, tb, 0, st>>>(d_x, n, d_out2);
         trpl_lse_sum_kernel<<<(unsigned)blocks, tb, 0, st>>>(d_x, n, d_out2);
     }
+    CK(cudaGetLastError());
+    return TRPL_OK;
+}
+
+
+int trpl_random_grid(double *d_x, int64_t S, int64_t ldx, const double *minx, const double *maxx,
+                     const int32_t *do_log, int ncol, int override_flags, uint64_t seed,
+                     uint64_t first_sample, int device, void *stream)
+{
+    if (!d_x || !minx || !maxx || !do_log || S < 0 || ncol < 1 || ncol > 16 || ldx < ncol) return TRPL_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (S == 0) return TRPL_OK;
+    GridArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    for (int j = 0; j < ncol; j++) {
+        if (!(minx[j] <= maxx[j]) || (do_log[j] && minx[j] != maxx[j] && !(minx[j] > 0))) return TRPL_EINVAL;
+        ga.lo[j] = minx[j]; ga.hi[j] = maxx[j]; ga.do_log[j] = do_log[j];
+    }
+    ga.ncol = ncol;
+    ga.eq_mu = (override_flags & 1) && ncol > 3;
+    ga.eq_s = (override_flags & 2) && ncol > 6;
+    ga.eq_auger = (override_flags & 4) && ncol > 8;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    const int tb = 256;
+    long long blocks = (S * ncol + tb - 1) / tb;
+    if (blocks > (long long)nsm * 16) blocks = (long long)nsm * 16;
+    trpl_random_grid_kernel<<<(unsigned)blocks, tb, 0, (cudaStream_t)stream>>>(d_x, S, ldx, ga, seed, first_sample);
+    CK(cudaGetLastError());
+    return TRPL_OK;
+}
+
+int trpl_posterior_weights(const double *d_lnp, int64_t n, double lse, double *d_w, int device, void *stream)
+{
+    if (!d_lnp || !d_w || n < 0) return TRPL_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n == 0) return TRPL_OK;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    const int tb = 256;
+    long long blocks = (n + tb - 1) / tb;
+    if (blocks > (long long)nsm * 16) blocks = (long long)nsm * 16;
+    trpl_weights_kernel<<<(unsigned)blocks, tb, 0, (cudaStream_t)stream>>>(d_lnp, n, lse, d_w);
+    CK(cudaGetLastError());
+    return TRPL_OK;
+}
+
+int trpl_weighted_hist(const double *d_x, int64_t n, int64_t ldx, int colx, int coly, const double *d_w,
+                       double lox, double hix, int nbx, double loy, double hiy, int nby, double *d_hist,
+                       int device, void *stream)
+{
+    if (!d_x || !d_hist || n < 0 || colx < 0 || colx >= ldx || coly >= ldx || nbx < 1 || !(hix > lox))
+        return TRPL_EINVAL;
+    if (coly >= 0 && (nby < 1 || !(hiy > loy))) return TRPL_EINVAL;
+    const long long nb = (long long)nbx * (coly >= 0 ? nby : 1);
+    if (nb > 8192) return TRPL_EUNSUPPORTED;
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n == 0) return TRPL_OK;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    const int tb = 256;
+    long long blocks = (n + tb - 1) / tb;
+    if (blocks > (long long)nsm * 4) blocks = (long long)nsm * 4;
+    const size_t smem = (size_t)nb * sizeof(double);
+    CK(cudaFuncSetAttribute((const void *)trpl_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    trpl_hist_kernel<<<(unsigned)blocks, tb, smem, (cudaStream_t)stream>>>(d_x, ldx, colx, coly, d_w, n, lox, hix,
+                                                                            nbx, loy, hiy, nby, d_hist);
+    CK(cudaGetLastError());
+    return TRPL_OK;
+}
+
+int trpl_weighted_moments(const double *d_x, int64_t n, int64_t ldx, int ncol, const double *d_w,
+                          double *d_out, int device, void *stream)
+{
+    if (!d_x || !d_w || !d_out || n < 0 || ncol < 1 || ncol > 15 || ldx < ncol) return TRPL_EINVAL;
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n == 0) return TRPL_OK;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    long long blocks = (n + 63) / 64;
+    if (blocks > (long long)nsm * 4) blocks = (long long)nsm * 4;
+    trpl_moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_x, ldx, ncol, d_w, n, d_out);
     CK(cudaGetLastError());
     return TRPL_OK;
 }

@@ -203,3 +203,51 @@ def bench_dfma(iters=20000, device=None):
     check(_lib.lib().trpl_bench_dfma(dev.index, int(iters), ctypes.byref(tf), ctypes.byref(ms)),
           "trpl_bench_dfma")
     return tf.value, ms.value
+
+
+def random_grid_device(minX, maxX, do_log, num_points, seed, first_sample=0, override_flags=0,
+                       device=None, out=None):
+    """bayeslib.random_grid/make_grid on the device (trpl_random_grid): X [num_points, ncol] CUDA tensor.
+    Counter-based, so rank r can generate rows [lo, hi) of the global draw with first_sample=lo."""
+    dev = require_cuda(device)
+    lo = np.ascontiguousarray(minX, dtype=np.float64)
+    hi = np.ascontiguousarray(maxX, dtype=np.float64)
+    dl = np.ascontiguousarray(do_log, dtype=np.int32)
+    ncol = lo.shape[0]
+    X = out if out is not None else torch.empty((num_points, ncol), dtype=torch.float64, device=dev)
+    rc = _lib.lib().trpl_random_grid(_ptr(X), num_points, X.stride(0) if num_points > 1 else ncol,
+                                     lo.ctypes.data_as(ctypes.c_void_p), hi.ctypes.data_as(ctypes.c_void_p),
+                                     dl.ctypes.data_as(ctypes.c_void_p), ncol, int(override_flags),
+                                     int(seed), int(first_sample), dev.index, _stream(dev))
+    check(rc, "trpl_random_grid")
+    return X
+
+
+def posterior_weights(lnp, lse):
+    """w = exp(lnP - lse) on the device (NaN -> 0)."""
+    assert lnp.is_cuda and lnp.dtype == torch.float64 and lnp.is_contiguous()
+    w = torch.empty_like(lnp)
+    check(_lib.lib().trpl_posterior_weights(_ptr(lnp), lnp.numel(), float(lse), _ptr(w),
+                                            lnp.device.index, _stream(lnp.device)), "trpl_posterior_weights")
+    return w
+
+
+def weighted_hist(X, colx, w, lox, hix, nbx, coly=-1, loy=0.0, hiy=1.0, nby=1, out=None):
+    """Raw weighted histogram (numpy.histogram / histogram2d binning) of column colx (x coly) of X."""
+    assert X.is_cuda and X.dtype == torch.float64 and X.stride(1) == 1
+    shape = (nbx,) if coly < 0 else (nbx, nby)
+    h = out if out is not None else torch.zeros(shape, dtype=torch.float64, device=X.device)
+    check(_lib.lib().trpl_weighted_hist(_ptr(X), X.shape[0], _row_stride(X), int(colx), int(coly), _ptr(w),
+                                        float(lox), float(hix), int(nbx), float(loy), float(hiy), int(nby),
+                                        _ptr(h), X.device.index, _stream(X.device)), "trpl_weighted_hist")
+    return h
+
+
+def weighted_moments(X, w, ncol=None, out=None):
+    """Raw sums [sum w, sum w x_j, sum w x_j x_k] of the first ncol columns of X."""
+    assert X.is_cuda and X.dtype == torch.float64 and X.stride(1) == 1
+    ncol = X.shape[1] if ncol is None else ncol
+    o = out if out is not None else torch.zeros(1 + ncol + ncol * ncol, dtype=torch.float64, device=X.device)
+    check(_lib.lib().trpl_weighted_moments(_ptr(X), X.shape[0], _row_stride(X), int(ncol), _ptr(w), _ptr(o),
+                                           X.device.index, _stream(X.device)), "trpl_weighted_moments")
+    return o

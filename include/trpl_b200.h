@@ -24,6 +24,10 @@
  *                        summed over curves)                                 bayeslib.py:117-201
  *   trpl_obs_prepare     scipy griddata/interp1d index+weight rule used at   bayeslib.py:186-189
  *   trpl_lse_partial     Visualization/utils.normalize (shifted exp / sum)   Visualization/utils.py:157-166
+ *   trpl_posterior_weights, trpl_weighted_hist, trpl_weighted_moments
+ *                        normalize / marginalize_1D / marginalize_2D / w_mean /
+ *                        w_variance / covariance                             Visualization/utils.py:157-285
+ *   trpl_random_grid     bayeslib.random_grid + make_grid overrides          bayeslib.py:18-76
  */
 #ifndef TRPL_B200_H
 #define TRPL_B200_H
@@ -133,6 +137,32 @@ int trpl_obs_prepare(const double *times, int32_t n, double time, int T,
 /* Shard-local part of the posterior normalisation: d_out[0] = max_i x_i, d_out[1] =
  * sum_i exp(x_i - max) over finite x (NaN skipped like numpy.nanmax/nansum).               */
 int trpl_lse_partial(const double *d_x, int64_t n, double *d_out2, int device, void *stream);
+
+/* Sample matrix on the device: X[s][j] uniform (or log-uniform where do_log[j]) in [minx[j], maxx[j]],
+ * constant where minx[j] == maxx[j]; counter-based Philox4x32-10 keyed by `seed`, sample index
+ * first_sample + s (so shards of one global draw can be generated independently on every rank).
+ * override_flags: bit0 X[:,2]=X[:,3] (equal mu), bit1 X[:,6]=X[:,5] (equal S), bit2 X[:,8]=X[:,7]
+ * (equal Auger), bayeslib.py:68-75.  minx/maxx/do_log are HOST arrays of ncol (<= 16) entries.   */
+int trpl_random_grid(double *d_x, int64_t S, int64_t ldx, const double *minx, const double *maxx,
+                     const int32_t *do_log, int ncol, int override_flags, uint64_t seed,
+                     uint64_t first_sample, int device, void *stream);
+
+/* d_w[i] = exp(d_lnp[i] - lse)  (NaN -> 0): posterior weights once lse = log sum exp is known.   */
+int trpl_posterior_weights(const double *d_lnp, int64_t n, double lse, double *d_w, int device,
+                           void *stream);
+
+/* Weighted histogram with numpy.histogram(2d) binning: nbx uniform bins on [lox, hix] of column
+ * colx (and nby bins on [loy, hiy] of column coly when coly >= 0; row-major [nbx][nby]).
+ * d_hist is ACCUMULATED into (zero it first); d_w == NULL counts samples.  Raw sums, no density
+ * normalisation (marginalize_1D/2D divide by sum*bin width on the host).                         */
+int trpl_weighted_hist(const double *d_x, int64_t n, int64_t ldx, int colx, int coly, const double *d_w,
+                       double lox, double hix, int nbx, double loy, double hiy, int nby, double *d_hist,
+                       int device, void *stream);
+
+/* Raw weighted moments, ACCUMULATED into d_out[1 + ncol + ncol*ncol]:
+ * [0] = sum w, [1+j] = sum w x_j, [1+ncol+j*ncol+k] = sum w x_j x_k  (ncol <= 15).               */
+int trpl_weighted_moments(const double *d_x, int64_t n, int64_t ldx, int ncol, const double *d_w,
+                          double *d_out, int device, void *stream);
 
 /* FP64 FMA-pipe microbenchmark (roofline denominator): runs `iters` dependent-chain DFMA
  * rounds on every SM and returns the achieved TFLOP/s (2 flop per FMA) in *tflops.

@@ -416,3 +416,122 @@ def test_fine_grid_fused_likelihood(trpl, oracle):
     torch.cuda.synchronize()
     assert (status.cpu().numpy() == 0).all()
     np.testing.assert_allclose(lnl.cpu().numpy(), ref, rtol=1e-6, atol=1e-9)
+
+
+def test_entry_script_end_to_end(trpl, oracle, tmp_path):
+    """EXC.csv + OBS.csv in, BAYRAN_P/X out: the whole reference workflow (parallel_bayes_gpu.py)
+    on files written in the reference formats; likelihood table checked against the oracle."""
+    L, T = 128, 300
+    Time = 0.025 * T
+    ex = example_data()
+    exc_path = str(tmp_path / "exc.csv")
+    with open(exc_path, "w") as fh:
+        for row in ex["power_exc"]:
+            fh.write(",".join("%.8E" % v for v in row) + ",\n")
+    inis = trpl.bayes_io.get_initpoints(exc_path, {"select_obs_sets": None})
+    simPar = [2000.0, Time, L, T, 1, (0,), 7, 10000]
+    grid = np.linspace(0, Time, T + 1)
+    pls = [oracle.solve((TRUTH * UC)[None, :12], simPar, inis[c], solver="thomas")["pl"][0] for c in range(3)]
+    obs_path = str(tmp_path / "obs.csv")
+    trpl.bayes_io.write_observations(obs_path, [grid] * 3, pls)
+    cfg = trpl.parallel_bayes_gpu.default_config()
+    cfg.update(Length=2000.0, Time=Time, T=T)
+    cfg["ic_flags"]["time_cutoff"] = Time
+    cfg["sim_flags"]["num_points"] = 12
+    cfg["gpu_info"]["sims_per_gpu"] = 5
+    out = str(tmp_path / "RUN")
+    P, X = trpl.parallel_bayes_gpu.run(exc_path, [obs_path], [out], cfg=cfg, posterior=True)
+    Pf = np.load(os.path.join(out, "RUN_BAYRAN_P.npy"))
+    Xf = np.load(os.path.join(out, "RUN_BAYRAN_X.npy"))
+    W = np.load(os.path.join(out, "RUN_BAYRAN_W.npy"))
+    assert Pf.shape == (12,) and Xf.shape == (12, 13)
+    np.testing.assert_array_equal(Pf, P[0])
+    # same draw as the reference sampler with seed 42
+    np.random.seed(42)
+    Xr = trpl.bayeslib.random_grid(cfg["minX"] * trpl.parallel_bayes_gpu.unit_conversions,
+                                   cfg["maxX"] * trpl.parallel_bayes_gpu.unit_conversions,
+                                   cfg["do_log"], 12)
+    np.testing.assert_allclose(Xf * trpl.parallel_bayes_gpu.unit_conversions, Xr, rtol=1e-15)
+    e_data = trpl.bayes_io.get_data([obs_path], cfg["ic_flags"], cfg["sim_flags"])
+    ref = oracle.loglik(Xr, simPar, inis, e_data, solver="pcr")
+    np.testing.assert_allclose(Pf, ref[0], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(W.sum(), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(W, np.exp(Pf - Pf.max()) / np.exp(Pf - Pf.max()).sum(), rtol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------
+# neighbours of the path: device-side sampling and posterior products
+# ------------------------------------------------------------------------------------------------
+def _philox4x32_10(c, k):
+    """numpy restatement of Philox4x32-10 (Salmon et al., Random123): c [n,4] uint32, k (k0,k1)."""
+    c = c.astype(np.uint64)
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    M0, M1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = c[:, 0], c[:, 1], c[:, 2], c[:, 3]
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & mask, lo1, (hi0 ^ c3 ^ k1) & mask, lo0
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack([c0, c1, c2, c3], axis=1)
+
+
+def test_device_random_grid_matches_numpy_philox(trpl):
+    from helpers import DO_LOG, MAXX, MINX
+    lo, hi = MINX * UC, MAXX * UC
+    lo[2:4] = 0.5 * UC[2:4]
+    S, seed, first = 5000, 0x1234567812345678, 7 * 2 ** 32 + 11
+    X = trpl.engine.random_grid_device(lo, hi, DO_LOG, S, seed, first_sample=first, override_flags=2).cpu().numpy()
+    ids = first + np.arange(S, dtype=np.uint64)
+    ref = np.empty((S, 13))
+    for j in range(13):
+        src = 5 if j == 6 else j                       # override_equal_s
+        c = np.stack([ids & np.uint64(0xFFFFFFFF), ids >> np.uint64(32),
+                      np.full(S, src, np.uint64), np.zeros(S, np.uint64)], axis=1)
+        r = _philox4x32_10(c, (seed & 0xFFFFFFFF, seed >> 32))
+        u = (((r[:, 0] << np.uint64(32)) | r[:, 1]) >> np.uint64(11)).astype(np.float64) / 2.0 ** 53
+        if lo[src] == hi[src]:
+            ref[:, j] = lo[src]
+        elif DO_LOG[src]:
+            a, b = np.log10(lo[src]), np.log10(hi[src])
+            ref[:, j] = 10 ** (a + (b - a) * u)
+        else:
+            ref[:, j] = lo[src] + (hi[src] - lo[src]) * u
+    np.testing.assert_allclose(X, ref, rtol=4e-15)
+    np.testing.assert_array_equal(X[:, 6], X[:, 5])
+    assert ((X >= lo * (1 - 1e-14)) & (X <= hi * (1 + 1e-14))).all()
+    # shards of one global draw are reproducible independently
+    Xb = trpl.engine.random_grid_device(lo, hi, DO_LOG, 100, seed, first_sample=first + 400, override_flags=2)
+    np.testing.assert_array_equal(Xb.cpu().numpy(), X[400:500])
+
+
+def test_posterior_products_match_numpy(trpl):
+    rng = np.random.default_rng(10)
+    S = 200003
+    X = rng.normal(size=(S, 13)) * np.arange(1, 14) + 3.0
+    lnP = -0.5 * ((X[:, 2] - 3.5) ** 2 + (X[:, 5] - 2.0) ** 2 / 4) - 4000.0
+    lnP[17] = np.nan
+    Xd, Ld = torch.from_numpy(X).cuda(), torch.from_numpy(lnP).cuda()
+    w = trpl.posterior.normalize(Ld)
+    wr = np.exp(lnP - np.nanmax(lnP)); wr[np.isnan(wr)] = 0; wr /= wr.sum()
+    np.testing.assert_allclose(w.cpu().numpy(), wr, rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(float(trpl.posterior.log_evidence(Ld)),
+                               np.nanmax(lnP) + np.log(np.nansum(np.exp(lnP - np.nanmax(lnP)))), rtol=1e-13)
+    dens, bins = trpl.posterior.marginalize_1D(w, Xd, 2, -9.0, 15.0, 96)
+    ref, rb = np.histogram(X[:, 2], weights=wr, bins=np.linspace(-9, 15, 97), density=True)
+    # numpy.histogram accumulates weights through a cumulative sum (absolute error ~eps*total), so
+    # its tail bins are noise; the device result is compared with an absolute floor for those
+    np.testing.assert_allclose(dens.cpu().numpy(), ref, rtol=1e-9, atol=1e-12 * ref.max())
+    exact = np.bincount(np.clip(((X[:, 2] + 9.0) / 0.25).astype(int), 0, 95)[(X[:, 2] >= -9) & (X[:, 2] <= 15)],
+                        weights=wr[(X[:, 2] >= -9) & (X[:, 2] <= 15)], minlength=96)
+    np.testing.assert_allclose(dens.cpu().numpy(), exact / (exact.sum() * 0.25), rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(bins.cpu().numpy(), rb, rtol=1e-14, atol=1e-14)
+    d2 = trpl.posterior.marginalize_2D(w, Xd, 2, 5, -9.0, 15.0, -20.0, 25.0, 32)
+    r2 = np.histogram2d(X[:, 2], X[:, 5], bins=[np.linspace(-9, 15, 33), np.linspace(-20, 25, 33)],
+                        weights=wr, density=True)[0]
+    np.testing.assert_allclose(d2.cpu().numpy(), r2, rtol=1e-9, atol=1e-300)
+    cnt = trpl.engine.weighted_hist(Xd, 0, None, -3.0, 9.0, 50).cpu().numpy()
+    np.testing.assert_array_equal(cnt, np.histogram(X[:, 0], bins=np.linspace(-3, 9, 51))[0])
+    mean, cov = trpl.posterior.moments(w, Xd)
+    np.testing.assert_allclose(mean.cpu().numpy(), np.average(X, axis=0, weights=wr), rtol=1e-10)
+    np.testing.assert_allclose(cov.cpu().numpy(), np.cov(X.T, aweights=wr, ddof=0), rtol=1e-7, atol=1e-9)
