@@ -119,10 +119,12 @@ struct Comm {
     int rphase;       // ping-pong selector of red
 
     // K values from lane g-dm (-> vm) and lane g+dp (-> vp); out-of-range sources return the
-    // caller's own value (always multiplied by an exact zero downstream).
+    // caller's own value (always multiplied by an exact zero downstream).  For W > 1 the barrier
+    // of the exchange also OR-reduces `busy` over the simulation (BAR.RED.OR) and returns it, so a
+    // block-wide vote costs no barrier of its own; W == 1 returns true.
     template <int K, bool WANT_M, bool WANT_P>
-    __device__ __forceinline__ void xchg(const double (&v)[K], const int dm, const int dp,
-                                         double (&vm)[K], double (&vp)[K])
+    __device__ __forceinline__ bool xchg(const double (&v)[K], const int dm, const int dp,
+                                         double (&vm)[K], double (&vp)[K], const bool busy = true)
     {
         if constexpr (W == 1) {
 #pragma unroll
@@ -130,12 +132,13 @@ struct Comm {
                 if (WANT_M) vm[k] = __shfl_up_sync(FULL, v[k], dm);
                 if (WANT_P) vp[k] = __shfl_down_sync(FULL, v[k], dp);
             }
+            return true;
         } else {
             constexpr int G = 32 * W;
             double *buf = xb + phase * (3 * G);
 #pragma unroll
             for (int k = 0; k < K; k++) buf[k * G + g] = v[k];
-            __syncthreads();
+            const bool any_busy = __syncthreads_or(busy) != 0;
             const int im = (g - dm >= 0) ? g - dm : g;
             const int ip = (g + dp < G) ? g + dp : g;
 #pragma unroll
@@ -144,6 +147,7 @@ struct Comm {
                 if (WANT_P) vp[k] = buf[k * G + ip];
             }
             phase ^= 1;
+            return any_busy;
         }
     }
     __device__ __forceinline__ double from_prev(const double v)     // value of lane g-1
@@ -214,10 +218,11 @@ struct Comm {
 // Tridiagonal solve, M rows per lane (row n = M*g + j):  l[j] x[n-1] + d[j] x[n] + u[j] x[n+1] = b[j].
 // Rows outside the physical system must be identity rows (l=u=0, d=1).  l of the first row
 // and u of the last physical row must be 0.
+// Returns the new value of the previous lane's last node (needed by the callers anyway).
 template <int M, int W>
-__device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double (&d)[M],
-                                              const double (&u)[M], const double (&b)[M],
-                                              double (&x)[M], Comm<W> &cm)
+__device__ __forceinline__ double tridiag_solve(const double (&l)[M], const double (&d)[M],
+                                                const double (&u)[M], const double (&b)[M],
+                                                double (&x)[M], Comm<W> &cm)
 {
     double Lr, Dr, Ur, Br;
     double c[M > 1 ? M - 1 : 1], y[M > 1 ? M - 1 : 1], v[M > 1 ? M - 1 : 1], w[M > 1 ? M - 1 : 1];
@@ -274,12 +279,15 @@ __device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double
     for (int rf = 1; rf < 32 * W; rf <<= 1) {
         // Off-diagonals shrink quadratically per stage; once every |L|,|U| of the simulation is
         // below 2^-70 the remaining stages cannot change D = 1 or B in the last bit: stop.
-        if (rf >= 2) {
-            const int hl = __double2hiint(Lr) & 0x7fffffff, hu = __double2hiint(Ur) & 0x7fffffff;
-            if (cm.all(max(hl, hu) < ((1023 - 70) << 20))) break;
-        }
+        const int hl = __double2hiint(Lr) & 0x7fffffff, hu = __double2hiint(Ur) & 0x7fffffff;
+        const bool busy = (rf < 2) || (max(hl, hu) >= ((1023 - 70) << 20));
         double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
-        cm.template xchg<3, true, true>(mine, rf, rf, vm, vp);
+        if constexpr (W == 1) {
+            if (rf >= 2 && !__any_sync(FULL, busy)) break;
+            cm.template xchg<3, true, true>(mine, rf, rf, vm, vp);
+        } else {
+            if (!cm.template xchg<3, true, true>(mine, rf, rf, vm, vp, busy)) break;
+        }
         const double Lm = vm[0], Um = vm[1], Bm = vm[2];
         const double Lp = vp[0], Up = vp[1], Bp = vp[2];
         const double D = fma(-Lp, Ur, fma(-Um, Lr, 1.0));
@@ -292,11 +300,12 @@ __device__ __forceinline__ void tridiag_solve(const double (&l)[M], const double
         Ur = Un * inv;
     }
     x[M - 1] = Br;
+    const double sl = cm.from_prev(Br);
     if constexpr (M > 1) {
-        const double sl = cm.from_prev(Br);
 #pragma unroll
         for (int j = 0; j < M - 1; j++) x[j] = fma(-w[j], Br, fma(-v[j], sl, y[j]));
     }
+    return sl;
 }
 
 // lane-private ring of the 4 older BDF levels: [slot 0..3][field N,P,E][M doubles per lane]
@@ -635,8 +644,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     rN += fabs(res);
                     sbN += fabs(b[j]);
                 }
-                tridiag_solve<M, W>(l, d, u, b, N, cm);
-                Nl = cm.from_prev(N[M - 1]);
+                Nl = tridiag_solve<M, W>(l, d, u, b, N, cm);
                 Nr = cm.from_next(N[0]);
             }
 
@@ -699,8 +707,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 // known here, before the P solve; reducing them now lets the shuffle chain overlap
                 // the solve.
                 cm.stop_rule(rN, sbN, rP, sbP, TOL, converged_now, nonfinite_now);
-                tridiag_solve<M, W>(l, d, u, b, P, cm);
-                Pl = cm.from_prev(P[M - 1]);
+                Pl = tridiag_solve<M, W>(l, d, u, b, P, cm);
                 Pr = cm.from_next(P[0]);
             }
 
