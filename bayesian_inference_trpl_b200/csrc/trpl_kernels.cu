@@ -836,23 +836,37 @@ __global__ void trpl_finish_kernel(const double *sse, double *lnl, const int *st
 }
 
 // ---- probs.fastlog / log_kernel (probs.py:64-85) ---------------------------------------------
+// HBM-bound streaming kernels: 4 independent loads in flight per thread (memory-level parallelism).
 __global__ void trpl_log10_kernel_f64(double *x, long long n, double mn)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        double v0 = x[i], v1 = x[i + stride], v2 = x[i + 2 * stride], v3 = x[i + 3 * stride];
+        v0 = v0 < mn ? mn : v0; v1 = v1 < mn ? mn : v1; v2 = v2 < mn ? mn : v2; v3 = v3 < mn ? mn : v3;
+        x[i] = log10(v0); x[i + stride] = log10(v1); x[i + 2 * stride] = log10(v2); x[i + 3 * stride] = log10(v3);
+    }
+    for (; i < n; i += stride) {
         double v = x[i];
         if (v < mn) v = mn;
         x[i] = log10(v);
     }
 }
+__device__ __forceinline__ float log10_clamp_f32(float v, double mn)
+{
+    if ((double)v < mn) v = (float)mn;
+    return log10f(v);
+}
 __global__ void trpl_log10_kernel_f32(float *x, long long n, double mn)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
-        float v = x[i];
-        if ((double)v < mn) v = (float)mn;
-        x[i] = log10f(v);
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const float v0 = x[i], v1 = x[i + stride], v2 = x[i + 2 * stride], v3 = x[i + 3 * stride];
+        x[i] = log10_clamp_f32(v0, mn); x[i + stride] = log10_clamp_f32(v1, mn);
+        x[i + 2 * stride] = log10_clamp_f32(v2, mn); x[i + 3 * stride] = log10_clamp_f32(v3, mn);
     }
+    for (; i < n; i += stride) x[i] = log10_clamp_f32(x[i], mn);
 }
 
 // ---- probs.prob / kernel_lnP (probs.py:20-62): one warp per sample, coalesced row reads -------
@@ -865,13 +879,19 @@ __global__ void trpl_lnp_kernel(double *P, const double *pl, long long S, long l
     for (long long j = warp; j < S; j += nwarps) {
         const double m = mag[j];
         const double *row = pl + j * ld;
-        double acc = 0.0;
-        for (long long i = lane; i < n; i += 32) {
-            double err = row[i] + m;
-            err -= values[i];
-            acc = fma(err, err, acc);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        long long i = lane;
+        for (; i + 96 < n; i += 128) {
+            const double r0 = row[i], r1 = row[i + 32], r2 = row[i + 64], r3 = row[i + 96];
+            const double e0 = (r0 + m) - values[i], e1 = (r1 + m) - values[i + 32];
+            const double e2 = (r2 + m) - values[i + 64], e3 = (r3 + m) - values[i + 96];
+            a0 = fma(e0, e0, a0); a1 = fma(e1, e1, a1); a2 = fma(e2, e2, a2); a3 = fma(e3, e3, a3);
         }
-        acc = warp_sum(acc);
+        for (; i < n; i += 32) {
+            const double e = (row[i] + m) - values[i];
+            a0 = fma(e, e, a0);
+        }
+        const double acc = warp_sum((a0 + a1) + (a2 + a3));
         if (lane == 0) P[j] += (0.0 - acc);
     }
 }
@@ -1030,35 +1050,103 @@ __global__ void trpl_hist_kernel(const double *x, long long ldx, int colx, int c
 }
 
 // out[0] = sum w, out[1+j] = sum w x_j, out[1+ncol+j*ncol+k] = sum w x_j x_k
+// One thread per sample row (coalescing comes from the 32 rows of a warp being adjacent in
+// memory and ncol <= 15 columns being read in order); accumulators live in shared memory per
+// warp and are reduced with shuffles -> few atomics.
 __global__ void trpl_moments_kernel(const double *x, long long ldx, int ncol, const double *w,
                                     long long n, double *out)
 {
-    constexpr int TILE = 64;
-    __shared__ double tx[TILE][17];
-    __shared__ double tw[TILE];
     const int nacc = 1 + ncol + ncol * ncol;
-    const int a = threadIdx.x;
-    int j = -1, k = -1;
-    if (a >= 1 && a < 1 + ncol) j = a - 1;
-    else if (a >= 1 + ncol && a < nacc) { j = (a - 1 - ncol) / ncol; k = (a - 1 - ncol) % ncol; }
-    double acc = 0.0;
-    for (long long base = (long long)blockIdx.x * TILE; base < n; base += (long long)gridDim.x * TILE) {
-        const int rows = (int)((n - base < TILE) ? (n - base) : TILE);
-        __syncthreads();
-        for (int i = threadIdx.x; i < rows * ncol; i += blockDim.x)
-            tx[i / ncol][i % ncol] = x[(base + i / ncol) * ldx + (i % ncol)];
-        for (int i = threadIdx.x; i < rows; i += blockDim.x) tw[i] = w[base + i];
-        __syncthreads();
-        if (a < nacc) {
-            for (int r = 0; r < rows; r++) {
-                const double ww = tw[r];
-                if (a == 0) acc += ww;
-                else if (k < 0) acc = fma(ww, tx[r][j], acc);
-                else acc = fma(ww * tx[r][j], tx[r][k], acc);
+    extern __shared__ double acc_sh[];          // [nacc] per block
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) acc_sh[i] = 0.0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double sw = 0.0, sx[15], sxx[15];           // per thread: sum w, sum w x_j, and ONE row of x x^T at a time
+#pragma unroll
+    for (int j = 0; j < 15; j++) { sx[j] = 0.0; sxx[j] = 0.0; }
+    // pass structure: for each j0, accumulate sum w x_j0 x_k for all k (re-reading the row from L1/L2)
+    for (int j0 = -1; j0 < ncol; j0++) {
+#pragma unroll
+        for (int k = 0; k < 15; k++) sxx[k] = 0.0;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+            const double ww = w[i];
+            const double *row = x + i * ldx;
+            if (j0 < 0) {
+                sw += ww;
+#pragma unroll
+                for (int k = 0; k < 15; k++) if (k < ncol) sx[k] = fma(ww, row[k], sx[k]);
+            } else {
+                const double wx = ww * row[j0];
+#pragma unroll
+                for (int k = 0; k < 15; k++) if (k < ncol) sxx[k] = fma(wx, row[k], sxx[k]);
+            }
+        }
+        if (j0 < 0) {
+            sw = warp_sum(sw);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&acc_sh[0], sw);
+#pragma unroll
+            for (int k = 0; k < 15; k++) if (k < ncol) {
+                const double t = warp_sum(sx[k]);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&acc_sh[1 + k], t);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 15; k++) if (k < ncol) {
+                const double t = warp_sum(sxx[k]);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&acc_sh[1 + ncol + j0 * ncol + k], t);
             }
         }
     }
-    if (a < nacc && acc != 0.0) atomicAdd(&out[a], acc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x)
+        if (acc_sh[i] != 0.0) atomicAdd(&out[i], acc_sh[i]);
+}
+
+// Single-pass variant for the usual sample matrix (NC columns known at compile time): one thread per
+// row, sum w / sum w x_j / upper triangle of sum w x_j x_k in registers, one warp reduction at the end.
+template <int NC>
+__global__ void __launch_bounds__(128, 2)
+trpl_moments_kernel_fixed(const double *x, long long ldx, const double *w, long long n, double *out)
+{
+    constexpr int NT = NC * (NC + 1) / 2;
+    double sw = 0.0, sx[NC], sxx[NT];
+#pragma unroll
+    for (int j = 0; j < NC; j++) sx[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NT; j++) sxx[j] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ww = w[i];
+        double r[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) r[j] = x[i * ldx + j];
+        sw += ww;
+        int q = 0;
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const double wx = ww * r[j];
+            sx[j] += wx;
+#pragma unroll
+            for (int k = j; k < NC; k++) sxx[q++] = fma(wx, r[k], sxx[q]);
+        }
+    }
+    const bool lead = (threadIdx.x & 31) == 0;
+    sw = warp_sum(sw);
+    if (lead && sw != 0.0) atomicAdd(&out[0], sw);
+    int q = 0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const double t = warp_sum(sx[j]);
+        if (lead && t != 0.0) atomicAdd(&out[1 + j], t);
+#pragma unroll
+        for (int k = j; k < NC; k++) {
+            const double u = warp_sum(sxx[q++]);
+            if (lead && u != 0.0) {
+                atomicAdd(&out[1 + NC + j * NC + k], u);
+                if (k != j) atomicAdd(&out[1 + NC + k * NC + j], u);
+            }
+        }
+    }
 }
 
 // ---- FP64 FMA pipe microbenchmark ------------------------------------------------------------
@@ -1516,9 +1604,20 @@ int trpl_weighted_moments(const double *d_x, int64_t n, int64_t ldx, int ncol, c
     if (n == 0) return TRPL_OK;
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-    long long blocks = (n + 63) / 64;
-    if (blocks > (long long)nsm * 4) blocks = (long long)nsm * 4;
-    trpl_moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_x, ldx, ncol, d_w, n, d_out);
+    if (ncol == 13 || ncol == 12) {
+        long long nb = (n + 127) / 128;
+        if (nb > (long long)nsm * 2) nb = (long long)nsm * 2;
+        if (ncol == 13)
+            trpl_moments_kernel_fixed<13><<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(d_x, ldx, d_w, n, d_out);
+        else
+            trpl_moments_kernel_fixed<12><<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(d_x, ldx, d_w, n, d_out);
+        CK(cudaGetLastError());
+        return TRPL_OK;
+    }
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)nsm * 8) blocks = (long long)nsm * 8;
+    const size_t smem = (size_t)(1 + ncol + ncol * ncol) * sizeof(double);
+    trpl_moments_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d_x, ldx, ncol, d_w, n, d_out);
     CK(cudaGetLastError());
     return TRPL_OK;
 }

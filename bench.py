@@ -180,13 +180,25 @@ def main():
         exchange(lnl)
         return lnl, status, iters
 
+    # end to end = the call a user of the reference makes: bayeslib.simulate(model, e_data, P, X, ...)
+    # with HOST numpy arrays (bayeslib.py:83); per call it stages X, the excitations and the
+    # bracketed observations to the device, runs the fused kernel and reads lnL back into P.
+    sim_flags = {"load_PL_from_file": False, "log_pl": True, "self_normalize": False}
+    gpu_info = {"has_GPU": True, "sims_per_gpu": S, "num_gpus": 1, "device": local,
+                "threads_per_block": (128,), "max_sims_per_block": 1}
+    P_host = np.zeros((1, S))
+    obs_bytes = sum(len(t) * (4 + 8 + 8 + 8) for t in ts)
+    h2d_bytes = int(X.size * 8 + inis.size * 8 + obs_bytes)
+    d2h_bytes = int(S * 8 + S * 4)
+
     def step_e2e():
-        Xd.copy_(X_pin, non_blocking=True)
-        lnl, status, _ = trpl.engine.solve_loglik(Xd, problem)
-        full = exchange(lnl)
-        lnl_host.copy_(lnl, non_blocking=True)
-        torch.cuda.synchronize(dev)
-        return lnl_host
+        P_host[:] = 0.0
+        tm = [np.zeros(1), np.zeros(1), np.zeros(1)]
+        trpl.bayeslib.simulate(trpl.pvSim, e_data, P_host, X, [None], [None], 3, list(SIMPAR), inis,
+                               sim_flags, gpu_info, 0, tm[0], tm[1], tm[2])
+        if world > 1:
+            exchange(torch.from_numpy(P_host).to(dev))
+        return P_host
 
     def barrier():
         if world > 1:
@@ -258,8 +270,9 @@ def main():
                        "nonconverged_samples": n_bad,
                        "mean_newton_iters_per_step": float(iters_total.sum() / (3.0 * S * (T + 1)))},
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(X_pin.numel() * 8),
-                    "d2h_bytes_per_step": int(S * 8)},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes,
+                    "api": "bayeslib.simulate(model, e_data, P, X, ...) with host numpy arrays"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": None,
