@@ -261,6 +261,11 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None
+        try:   # DRAM bytes of one bench-sized launch, from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -273,9 +278,9 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes,
                     "api": "bayeslib.simulate(model, e_data, P, X, ...) with host numpy arrays"},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": (2 + (3 if world > 1 else 0)) * args.steps,   # sim + finish (+ 3 lse kernels when sharded)
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": None,
+                         "frac": achieved / tf_peak, "traffic": traffic,
                          "kernel": "trpl_sim_kernel<4,false>", "kernel_ms": kern_mean,
                          "flops_per_launch": flops_per_step,
                          "peak_source": "DFMA microbenchmark (trpl_bench_dfma) measured in this run; "
