@@ -82,6 +82,13 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(n_samples, threads):
     """Oracle (port of the reference algorithm, Thomas solve) on `threads` host threads."""
     from oracle import oracle
@@ -98,7 +105,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle
-    threads = oracle.num_threads()
+    threads = host_threads()          # torchrun pins OMP_NUM_THREADS=1; use every core the process may run on
     n = max(threads, 1)
     for _ in range(args.warmup if args.warmup < 1 else 1):
         cpu_baseline(max(1, threads // 4), threads)
@@ -289,8 +296,7 @@ def main():
                          "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
         }
         if not args.no_cpu_baseline and world == 1:
-            from oracle import oracle
-            threads = oracle.num_threads()
+            threads = host_threads()
             v, dt = cpu_baseline(threads, threads)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": "%d samples x 3 curves at full T=80000 (%.1f s), oracle "
