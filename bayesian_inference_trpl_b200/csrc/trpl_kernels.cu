@@ -181,37 +181,32 @@ struct Comm {
         }
         return v;
     }
-    // stop rule: errN = rN/sbN < TOL and errP = rP/sbP < TOL  (pvSimPCR.py:213-216)
-    __device__ __forceinline__ void stop_rule(const double rN, const double sbN, const double rP,
-                                              const double sbP, const double TOL, bool &converged,
+    // stop rule errN < TOL and errP < TOL (pvSimPCR.py:213-216) with err = sum|res| / sum|b|, evaluated
+    // division-free as z = sum(|res| - TOL*|b|) < 0 for both species (one 2-value butterfly).
+    __device__ __forceinline__ void stop_rule(const double zN, const double zP, bool &converged,
                                               bool &nonfinite)
     {
         const int lane = threadIdx.x & 31;
-        const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
-        double k0 = hi16 ? sbN : rN, k1 = hi16 ? sbP : rP;
-        const double s0 = hi16 ? rN : sbN, s1 = hi16 ? rP : sbP;
-        k0 += __shfl_xor_sync(FULL, s0, 16);
-        k1 += __shfl_xor_sync(FULL, s1, 16);
-        double k = hi8 ? k1 : k0;
-        const double sd = hi8 ? k0 : k1;
-        k += __shfl_xor_sync(FULL, sd, 8);
+        const bool hi16 = (lane & 16) != 0;
+        double k = hi16 ? zP : zN;
+        const double sd = hi16 ? zN : zP;
+        k += __shfl_xor_sync(FULL, sd, 16);
+        k += __shfl_xor_sync(FULL, k, 8);
         k += __shfl_xor_sync(FULL, k, 4);
         k += __shfl_xor_sync(FULL, k, 2);
         k += __shfl_xor_sync(FULL, k, 1);
-        // lanes 0-7: sum rN, 8-15: sum rP, 16-23: sum |bN|, 24-31: sum |bP|  (of this warp)
+        // lanes 0-15: zN of this warp, lanes 16-31: zP
         if constexpr (W > 1) {
             double *r = red + rphase * (W * 4);
-            if ((lane & 7) == 0) r[(threadIdx.x >> 5) * 4 + (lane >> 3)] = k;
+            if ((lane & 15) == 0) r[(threadIdx.x >> 5) * 4 + (lane >> 4)] = k;
             __syncthreads();
             k = 0.0;
 #pragma unroll
-            for (int w = 0; w < W; w++) k += r[w * 4 + (lane >> 3)];
+            for (int w = 0; w < W; w++) k += r[w * 4 + (lane >> 4)];
             rphase ^= 1;
         }
-        const double other = __shfl_xor_sync(FULL, k, 16);
-        const double err = k * rcp64(other);                       // lanes 0-7: errN, 8-15: errP
-        converged = (__ballot_sync(FULL, err < TOL) & 0xffffu) == 0xffffu;
-        nonfinite = (__ballot_sync(FULL, !(fabs(err) <= DBL_MAX)) & 0xffffu) != 0u;
+        converged = __all_sync(FULL, k < 0.0);
+        nonfinite = __any_sync(FULL, !(fabs(k) <= DBL_MAX));
     }
 };
 
@@ -584,7 +579,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
         bool nonfinite = false;
         for (;;) {
             double l[M], d[M], u[M], b[M];
-            double rN = 0.0, sbN = 0.0, rP = 0.0, sbP = 0.0;
+            double zN = 0.0, zP = 0.0;    // sum(|residual| - TOL*|b|): err < TOL  <=>  z < 0
             bool converged_now = false, nonfinite_now = false;
 
             // ======== N system (P, E frozen) ========
@@ -638,11 +633,10 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 // L1 residual of the current iterate                         (pvSimPCR.py:172, :14-40)
 #pragma unroll
                 for (int j = 0; j < M; j++) {
-                    const double cm = (j == 0) ? Nl : N[j - 1];
-                    const double cp = (j == M - 1) ? Nr : N[j + 1];
-                    const double res = fma(l[j], cm, fma(d[j], N[j], fma(u[j], cp, -b[j])));
-                    rN += fabs(res);
-                    sbN += fabs(b[j]);
+                    const double xm = (j == 0) ? Nl : N[j - 1];
+                    const double xp = (j == M - 1) ? Nr : N[j + 1];
+                    const double res = fma(l[j], xm, fma(d[j], N[j], fma(u[j], xp, -b[j])));
+                    zN = fma(-TOL, fabs(b[j]), zN + fabs(res));
                 }
                 Nl = tridiag_solve<M, W>(l, d, u, b, N, cm);
                 Nr = cm.from_next(N[0]);
@@ -697,16 +691,15 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 }
 #pragma unroll
                 for (int j = 0; j < M; j++) {
-                    const double cm = (j == 0) ? Pl : P[j - 1];
-                    const double cp = (j == M - 1) ? Pr : P[j + 1];
-                    const double res = fma(l[j], cm, fma(d[j], P[j], fma(u[j], cp, -b[j])));
-                    rP += fabs(res);
-                    sbP += fabs(b[j]);
+                    const double xm = (j == 0) ? Pl : P[j - 1];
+                    const double xp = (j == M - 1) ? Pr : P[j + 1];
+                    const double res = fma(l[j], xm, fma(d[j], P[j], fma(u[j], xp, -b[j])));
+                    zP = fma(-TOL, fabs(b[j]), zP + fabs(res));
                 }
                 // ---- stop decision for THIS iteration (pvSimPCR.py:213-216): both L1 residuals are
                 // known here, before the P solve; reducing them now lets the shuffle chain overlap
                 // the solve.
-                cm.stop_rule(rN, sbN, rP, sbP, TOL, converged_now, nonfinite_now);
+                cm.stop_rule(zN, zP, converged_now, nonfinite_now);
                 Pl = tridiag_solve<M, W>(l, d, u, b, P, cm);
                 Pr = cm.from_next(P[0]);
             }
