@@ -184,3 +184,24 @@ def test_two_rank_gloo_gather_and_logsumexp(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out.decode()
+
+
+def test_bayes_io_matches_reference_reader():
+    """bayes_io.get_data / get_initpoints vs the reference's own readers on the same files
+    (golden made by tests/golden/make_io_golden.py)."""
+    from bayesian_inference_trpl_b200 import bayes_io
+    g = golden("io_golden.npz")
+    obs, exc = os.path.join(GOLDEN, "io_obs.csv"), os.path.join(GOLDEN, "io_exc.csv")
+    cases = {"log": ({"time_cutoff": None, "select_obs_sets": None, "noise_level": None},
+                     {"log_pl": True, "self_normalize": False}),
+             "cut_sel": ({"time_cutoff": 0.126, "select_obs_sets": [0, 2], "noise_level": None},
+                         {"log_pl": True, "self_normalize": False}),
+             "norm_lin": ({"time_cutoff": None, "select_obs_sets": None, "noise_level": None},
+                          {"log_pl": False, "self_normalize": True})}
+    for name, (ic, sf) in cases.items():
+        e = bayes_io.get_data([obs], ic, sf, scale_f=1e-23)[0]
+        assert len(e[0]) == int(g[name + "_n"])
+        for k, part in enumerate(("t", "pl", "unc")):
+            for c in range(len(e[0])):
+                np.testing.assert_array_equal(np.asarray(e[k][c]), g["%s_%s%d" % (name, part, c)])
+        np.testing.assert_array_equal(bayes_io.get_initpoints(exc, ic), g[name + "_ini"])
