@@ -68,7 +68,8 @@ def interpolate_rows(sim_times, rows, times):
     hi = np.clip(np.searchsorted(sim_times, times), 1, len(sim_times) - 1)
     lo = hi - 1
     span = sim_times[hi] - sim_times[lo]
-    out = ((times - sim_times[lo]) / span) * rows[:, hi] + ((sim_times[hi] - times) / span) * rows[:, lo]
+    with np.errstate(invalid="ignore"):      # log10(0) = -inf rows give NaN, as in the reference (Q5)
+        out = ((times - sim_times[lo]) / span) * rows[:, hi] + ((sim_times[hi] - times) / span) * rows[:, lo]
     outside = (times < sim_times[0]) | (times > sim_times[-1])
     if outside.any():
         out[:, outside] = np.nan
