@@ -535,3 +535,37 @@ def test_posterior_products_match_numpy(trpl):
     mean, cov = trpl.posterior.moments(w, Xd)
     np.testing.assert_allclose(mean.cpu().numpy(), np.average(X, axis=0, weights=wr), rtol=1e-10)
     np.testing.assert_allclose(cov.cpu().numpy(), np.cov(X.T, aweights=wr, ddof=0), rtol=1e-7, atol=1e-9)
+
+
+def test_raw_cabi_binding_as_documented_in_integration_md(trpl, oracle):
+    """Call libtrpl_b200.so exactly the way INTEGRATION.md tells a reference maintainer to: plain
+    ctypes, raw device pointers, no helper from this package in between."""
+    import ctypes
+    lib = ctypes.CDLL(trpl._lib.LIB_PATH)
+    lib.trpl_solve_pl.restype = ctypes.c_int
+    lib.trpl_solve_pl.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_double, ctypes.c_double] + [ctypes.c_int] * 7 + \
+                                 [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    lib.trpl_error_string.restype = ctypes.c_char_p
+    L, T, length, Time = 64, 200, 900.0, 5.0
+    X = prior_samples(5, seed=64)
+    x = (np.arange(L) + 0.5) * (length / L)
+    ini = 3e17 * 1e-21 * np.exp(-6e-3 * x)
+    d_mat = torch.from_numpy(np.ascontiguousarray(X[:, :12])).cuda()
+    d_ini = torch.from_numpy(ini).cuda()
+    d_pl = torch.empty((5, T + 1), dtype=torch.float64, device="cuda")
+    d_st = torch.zeros(5, dtype=torch.int32, device="cuda")
+    rc = lib.trpl_solve_pl(d_mat.data_ptr(), 5, 12, d_ini.data_ptr(), length, Time, L, T, 1, 7, 10000, 5, 0,
+                           d_pl.data_ptr(), 0, T + 1, d_st.data_ptr(), None, 0, None)
+    assert rc == 0, lib.trpl_error_string(rc)
+    torch.cuda.synchronize()
+    ref = oracle.solve(X[:, :12], [length, Time, L, T, 1, (0,), 7, 10000], ini, solver="pcr")
+    np.testing.assert_allclose(d_pl.cpu().numpy(), ref["pl"], rtol=1e-8)
+    # argument errors come back as codes, not exceptions or crashes
+    assert lib.trpl_solve_pl(d_mat.data_ptr(), 5, 11, d_ini.data_ptr(), length, Time, L, T, 1, 7, 10000, 5, 0,
+                             d_pl.data_ptr(), 0, T + 1, None, None, 0, None) == -1
+    assert lib.trpl_solve_pl(d_mat.data_ptr(), 5, 12, d_ini.data_ptr(), length, Time, 70, T, 1, 7, 10000, 5, 0,
+                             d_pl.data_ptr(), 0, T + 1, None, None, 0, None) == -2
+    assert lib.trpl_solve_pl(d_mat.data_ptr(), 5, 12, d_ini.data_ptr(), length, Time, L, T, 1, 7, 10000, 5, 0,
+                             d_pl.data_ptr(), 0, T + 1, None, None, 99, None) == -4
