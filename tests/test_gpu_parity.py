@@ -569,3 +569,27 @@ def test_raw_cabi_binding_as_documented_in_integration_md(trpl, oracle):
                              d_pl.data_ptr(), 0, T + 1, None, None, 0, None) == -2
     assert lib.trpl_solve_pl(d_mat.data_ptr(), 5, 12, d_ini.data_ptr(), length, Time, L, T, 1, 7, 10000, 5, 0,
                              d_pl.data_ptr(), 0, T + 1, None, None, 99, None) == -4
+
+
+def test_degenerate_parameters_match_oracle(trpl, oracle):
+    """Corners of the reference prior: zero mobility (the entry script's minX, parallel_bayes_gpu.py:91),
+    zero surface velocity, no Auger, extreme lifetimes."""
+    L, T, length = 128, 600, 2000.0
+    simPar = [length, 0.025 * T, L, T, 1, (0,), 7, 10000]
+    X = np.tile(TRUTH * UC, (8, 1))
+    X[0, 2] = 0.0                       # mu_n = 0
+    X[1, 3] = 0.0                       # mu_p = 0
+    X[2, 2:4] = 0.0                     # no transport at all: diagonal systems
+    X[3, 5:7] = 0.0                     # S = 0
+    X[4, 7:9] = 0.0                     # no Auger
+    X[5, 9:11] = [1.0, 1.0]             # 1 ns lifetimes
+    X[6, 9:11] = [1e6, 1e6]             # essentially no SRH
+    X[7, 4] = 1e-15 * UC[4]             # negligible radiative rate
+    ini = power_scan_excitations()[2]
+    ref = oracle.solve(X[:, :12], simPar, ini, solver="pcr")
+    pl = np.empty((8, T + 1))
+    st = np.ones(8, dtype=np.int32)
+    trpl.pvSim(pl, None, None, None, X[:, :12], simPar, ini, (128,), 0, 1, init_mode="points", status_out=st)
+    np.testing.assert_array_equal(st, ref["status"])
+    assert (st == 0).all()
+    _assert_pl_close(pl, ref["pl"], X[:, :12], simPar, rtol=1e-8)
