@@ -41,9 +41,11 @@ class Curve(ctypes.Structure):
 
 def build(force=False, verbose=False):
     """Compile csrc/trpl_kernels.cu into libtrpl_b200.so for sm_100a (cross-compiles without a GPU)."""
-    hdr = os.path.join(INCLUDE, "trpl_b200.h")
+    csrc = os.path.dirname(SRC)
+    deps = [os.path.join(INCLUDE, "trpl_b200.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc)
+                                                     if f.endswith((".cu", ".cuh"))]
     if (not force and os.path.exists(LIB_PATH)
-            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(SRC), os.path.getmtime(hdr))):
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps)):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):

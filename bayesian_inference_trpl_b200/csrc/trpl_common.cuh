@@ -1,0 +1,82 @@
+// trpl_common.cuh -- argument structs shared by host and device code, and small device helpers.
+// Part of libtrpl_b200.so (see include/trpl_b200.h and trpl_kernels.cu for the overview).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+#include <limits.h>
+
+#include "trpl_b200.h"
+
+namespace trpl {
+
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS_PER_CTA = 4;
+#ifndef TRPL_MIN_CTAS
+#define TRPL_MIN_CTAS 4
+#endif
+
+struct ObsDev {
+    int n;
+    int pad_;
+    const int *hi;
+    const double *whi;
+    const double *wlo;
+    const double *val;
+};
+
+struct CurveDev {
+    double scales[TRPL_NPAR];
+    double init_mul;      // dx^3, or 1 when the profile is already in grid units
+    double redim;         // dx^2 * dt                         (pvSimPCR.py:393)
+    const double *init;   // [L]
+    void *pl_out;         // row base for sample 0, or nullptr
+    int t_last;           // last time index to integrate to (<= T)
+    int pad_;
+    ObsDev obs[TRPL_MAX_EXP];
+};
+
+struct KArgs {
+    const double *x;
+    long long ldx;
+    long long S;
+    long long pl_stride;
+    double TOL;
+    double *sse;                 // [E][C][S] or nullptr
+    int *status;                 // [C][S] or nullptr
+    long long *iters;            // [C][S] or nullptr
+    unsigned long long *counter; // work-item counter (zeroed by the host)
+    int mag_col;                 // < 0: no magnitude offset
+    int C, E, L, plT, max_iter, max_order, flags, pl_dtype;
+    CurveDev curves[TRPL_MAX_CURVES];
+};
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp64(double x)
+{
+    // MUFU.RCP64H seed (rel. error <= 1e-6, measured on B200 with tools/microbench.cu) followed by
+    // one cubically convergent step r*(1 + e + e^2): max error 1 ulp (2.2e-16, measured over 2^24
+    // operands in four magnitude ranges).  No slow path: operands here are normal, finite and far
+    // from the exponent limits.
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    return fma(r, e, r);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
+
+
+}  // namespace trpl

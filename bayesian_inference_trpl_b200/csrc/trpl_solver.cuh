@@ -1,0 +1,718 @@
+// trpl_solver.cuh -- the forward-model + fused-likelihood kernels (the hot path):
+// Comm<W> (lane communication policy), tridiag_solve, Ring, run_sim, trpl_sim_kernel<M,PAD>,
+// trpl_sim_cta_kernel<W>.  Replaces pvSimPCR.py:14-293 and bayeslib.py:150-196.
+#pragma once
+#include "trpl_common.cuh"
+
+namespace trpl {
+
+// ---------------------------------------------------------------------------------------------
+// Communication among the lanes that share one simulation.  W = warps per simulation.
+//   W == 1: warp shuffles / votes only (the production path for L <= 256).
+//   W  > 1: one CTA of W warps per simulation (fine grids, L up to 128*W); values travel through a
+//           ping-pong exchange buffer in shared memory, one __syncthreads per exchange.  Every
+//           thread of the CTA executes the same sequence of exchanges.
+// g = index of this lane among the 32*W lanes of the simulation.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+struct Comm {
+    int g;            // lane index within the simulation
+    double *xb;       // W > 1: exchange buffer [2][3][G] doubles
+    double *red;      // W > 1: reduction scratch [2][W][4] doubles
+    int phase;        // ping-pong selector of xb
+    int rphase;       // ping-pong selector of red
+
+    // K values from lane g-dm (-> vm) and lane g+dp (-> vp); out-of-range sources return the
+    // caller's own value (always multiplied by an exact zero downstream).  For W > 1 the barrier
+    // of the exchange also OR-reduces `busy` over the simulation (BAR.RED.OR) and returns it, so a
+    // block-wide vote costs no barrier of its own; W == 1 returns true.
+    template <int K, bool WANT_M, bool WANT_P>
+    __device__ __forceinline__ bool xchg(const double (&v)[K], const int dm, const int dp,
+                                         double (&vm)[K], double (&vp)[K], const bool busy = true)
+    {
+        if constexpr (W == 1) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (WANT_M) vm[k] = __shfl_up_sync(FULL, v[k], dm);
+                if (WANT_P) vp[k] = __shfl_down_sync(FULL, v[k], dp);
+            }
+            return true;
+        } else {
+            constexpr int G = 32 * W;
+            double *buf = xb + phase * (3 * G);
+#pragma unroll
+            for (int k = 0; k < K; k++) buf[k * G + g] = v[k];
+            const bool any_busy = __syncthreads_or(busy) != 0;
+            const int im = (g - dm >= 0) ? g - dm : g;
+            const int ip = (g + dp < G) ? g + dp : g;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (WANT_M) vm[k] = buf[k * G + im];
+                if (WANT_P) vp[k] = buf[k * G + ip];
+            }
+            phase ^= 1;
+            return any_busy;
+        }
+    }
+    __device__ __forceinline__ double from_prev(const double v)     // value of lane g-1
+    {
+        double a[1] = {v}, m[1], p_[1];
+        xchg<1, true, false>(a, 1, 1, m, p_);
+        return m[0];
+    }
+    __device__ __forceinline__ double from_next(const double v)     // value of lane g+1
+    {
+        double a[1] = {v}, m[1], p_[1];
+        xchg<1, false, true>(a, 1, 1, m, p_);
+        return p_[0];
+    }
+    __device__ __forceinline__ bool all(const bool pred)
+    {
+        if constexpr (W == 1) return __all_sync(FULL, pred);
+        else return __syncthreads_and(pred) != 0;
+    }
+    __device__ __forceinline__ double sum(double v)                 // total over the simulation
+    {
+        v = warp_sum(v);
+        if constexpr (W > 1) {
+            double *r = red + rphase * (W * 4);
+            if ((threadIdx.x & 31) == 0) r[(threadIdx.x >> 5) * 4] = v;
+            __syncthreads();
+            v = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; w++) v += r[w * 4];
+            rphase ^= 1;
+        }
+        return v;
+    }
+    // stop rule errN < TOL and errP < TOL (pvSimPCR.py:213-216) with err = sum|res| / sum|b|, evaluated
+    // division-free as z = sum(|res| - TOL*|b|) < 0 for both species (one 2-value butterfly).
+    __device__ __forceinline__ void stop_rule(const double zN, const double zP, bool &converged,
+                                              bool &nonfinite)
+    {
+        const int lane = threadIdx.x & 31;
+        const bool hi16 = (lane & 16) != 0;
+        double k = hi16 ? zP : zN;
+        const double sd = hi16 ? zN : zP;
+        k += __shfl_xor_sync(FULL, sd, 16);
+        k += __shfl_xor_sync(FULL, k, 8);
+        k += __shfl_xor_sync(FULL, k, 4);
+        k += __shfl_xor_sync(FULL, k, 2);
+        k += __shfl_xor_sync(FULL, k, 1);
+        // lanes 0-15: zN of this warp, lanes 16-31: zP
+        if constexpr (W > 1) {
+            double *r = red + rphase * (W * 4);
+            if ((lane & 15) == 0) r[(threadIdx.x >> 5) * 4 + (lane >> 4)] = k;
+            __syncthreads();
+            k = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; w++) k += r[w * 4 + (lane >> 4)];
+            rphase ^= 1;
+        }
+        converged = __all_sync(FULL, k < 0.0);
+        nonfinite = __any_sync(FULL, !(fabs(k) <= DBL_MAX));
+    }
+};
+
+// Tridiagonal solve, M rows per lane (row n = M*g + j):  l[j] x[n-1] + d[j] x[n] + u[j] x[n+1] = b[j].
+// Rows outside the physical system must be identity rows (l=u=0, d=1).  l of the first row
+// and u of the last physical row must be 0.
+// Returns the new value of the previous lane's last node (needed by the callers anyway).
+template <int M, int W>
+__device__ __forceinline__ double tridiag_solve(const double (&l)[M], const double (&d)[M],
+                                                const double (&u)[M], const double (&b)[M],
+                                                double (&x)[M], Comm<W> &cm)
+{
+    double Lr, Dr, Ur, Br;
+    double c[M > 1 ? M - 1 : 1], y[M > 1 ? M - 1 : 1], v[M > 1 ? M - 1 : 1], w[M > 1 ? M - 1 : 1];
+    if constexpr (M > 1) {
+        // interior rows 0..M-2:  x_j = y_j - v_j * s_left - w_j * s_own
+        // Pivot reciprocals from the leading principal minors m_{j+1} = d_j m_j - l_j u_{j-1} m_{j-1}
+        // (1/pivot_j = m_j / m_{j+1}): the M-1 reciprocals are independent of each other, so
+        // their MUFU+Newton chains overlap instead of forming one serial chain.
+        double ip[M - 1];
+        {
+            double mm[M];                 // mm[j] = m_{j+1}
+            mm[0] = d[0];
+            if constexpr (M > 2) mm[1] = fma(d[1], d[0], -(l[1] * u[0]));
+#pragma unroll
+            for (int j = 2; j < M - 1; j++) mm[j] = fma(d[j], mm[j - 1], -((l[j] * u[j - 1]) * mm[j - 2]));
+            ip[0] = rcp64(mm[0]);
+#pragma unroll
+            for (int j = 1; j < M - 1; j++) ip[j] = mm[j - 1] * rcp64(mm[j]);
+        }
+        c[0] = u[0] * ip[0];
+        y[0] = b[0] * ip[0];
+        v[0] = l[0] * ip[0];
+#pragma unroll
+        for (int j = 1; j < M - 1; j++) {
+            c[j] = u[j] * ip[j];
+            y[j] = fma(-l[j], y[j - 1], b[j]) * ip[j];
+            v[j] = (-l[j] * v[j - 1]) * ip[j];
+        }
+        w[M - 2] = c[M - 2];
+#pragma unroll
+        for (int j = M - 3; j >= 0; j--) {
+            y[j] = fma(-c[j], y[j + 1], y[j]);
+            v[j] = fma(-c[j], v[j + 1], v[j]);
+            w[j] = -c[j] * w[j + 1];
+        }
+        // interface row (local M-1) couples s_left, s_own and the next lane's first interior row
+        double mine[3] = {y[0], v[0], w[0]}, nm[3], nx[3];
+        cm.template xchg<3, false, true>(mine, 1, 1, nm, nx);
+        const double y0n = nx[0], v0n = nx[1], w0n = nx[2];
+        const double lr = l[M - 1], ur = u[M - 1];
+        Lr = -lr * v[M - 2];
+        Dr = fma(-ur, v0n, fma(-lr, w[M - 2], d[M - 1]));
+        Ur = -ur * w0n;
+        Br = fma(-ur, y0n, fma(-lr, y[M - 2], b[M - 1]));
+    } else {
+        Lr = l[0]; Dr = d[0]; Ur = u[0]; Br = b[0];
+    }
+    // parallel cyclic reduction over the 32*W interface unknowns, unit diagonal
+    {
+        double inv = rcp64(Dr);
+        Lr *= inv; Ur *= inv; Br *= inv;
+    }
+#pragma unroll
+    for (int rf = 1; rf < 32 * W; rf <<= 1) {
+        // Off-diagonals shrink quadratically per stage; once every |L|,|U| of the simulation is
+        // below 2^-70 the remaining stages cannot change D = 1 or B in the last bit: stop.
+        const int hl = __double2hiint(Lr) & 0x7fffffff, hu = __double2hiint(Ur) & 0x7fffffff;
+        const bool busy = (rf < 2) || (max(hl, hu) >= ((1023 - 70) << 20));
+        double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
+        if constexpr (W == 1) {
+            if (rf >= 2 && !__any_sync(FULL, busy)) break;
+            cm.template xchg<3, true, true>(mine, rf, rf, vm, vp);
+        } else {
+            if (!cm.template xchg<3, true, true>(mine, rf, rf, vm, vp, busy)) break;
+        }
+        const double Lm = vm[0], Um = vm[1], Bm = vm[2];
+        const double Lp = vp[0], Up = vp[1], Bp = vp[2];
+        const double D = fma(-Lp, Ur, fma(-Um, Lr, 1.0));
+        const double B = fma(-Bp, Ur, fma(-Bm, Lr, Br));
+        const double Ln = -Lm * Lr;
+        const double Un = -Up * Ur;
+        const double inv = rcp64(D);
+        Br = B * inv;
+        Lr = Ln * inv;
+        Ur = Un * inv;
+    }
+    x[M - 1] = Br;
+    const double sl = cm.from_prev(Br);
+    if constexpr (M > 1) {
+#pragma unroll
+        for (int j = 0; j < M - 1; j++) x[j] = fma(-w[j], Br, fma(-v[j], sl, y[j]));
+    }
+    return sl;
+}
+
+// lane-private ring of the 4 older BDF levels: [slot 0..3][field N,P,E][M doubles per lane]
+template <int M>
+struct Ring {
+    double *base;   // warp base + lane offset
+    // element (slot, field, j): chunks of 2 doubles per lane keep 16-byte accesses conflict-free
+    __device__ __forceinline__ void load(int slot, int field, double (&h)[M]) const
+    {
+        if constexpr (M == 1) {
+            h[0] = base[(slot * 3 + field) * 32];
+        } else {
+#pragma unroll
+            for (int q = 0; q < M / 2; q++) {
+                const double2 t = *reinterpret_cast<const double2 *>(
+                    base + ((slot * 3 + field) * (M / 2) + q) * 64);
+                h[2 * q] = t.x;
+                h[2 * q + 1] = t.y;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(int slot, int field, const double (&h)[M]) const
+    {
+        if constexpr (M == 1) {
+            base[(slot * 3 + field) * 32] = h[0];
+        } else {
+#pragma unroll
+            for (int q = 0; q < M / 2; q++)
+                *reinterpret_cast<double2 *>(base + ((slot * 3 + field) * (M / 2) + q) * 64) =
+                    make_double2(h[2 * q], h[2 * q + 1]);
+        }
+    }
+};
+
+struct WarpScratch {      // per-warp shared scratch touched once every 32 PL samples
+    double sse[TRPL_MAX_EXP];
+    int pos[TRPL_MAX_EXP];
+};
+
+// ---------------------------------------------------------------------------------------------
+// one (sample, curve) simulation, executed by W warps (W == 1: one warp; W > 1: one CTA)
+// ---------------------------------------------------------------------------------------------
+template <int M, bool PAD, int W>
+__device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long long s,
+                                        double *ring_warp, WarpScratch *ws, const int lane,
+                                        Comm<W> &cm)
+{
+    constexpr int G = 32 * W;
+    const int g = cm.g;                         // lane index within the simulation
+    const bool io_warp = (W == 1) || (g < 32);  // the warp that stages, stores and scores PL
+    const CurveDev &cv = a.curves[c];
+    const int L = a.L;
+    const int flags = a.flags;
+    const bool emu32 = (flags & TRPL_F_EMULATE_F32) != 0;
+
+    // ---- parameters: non-dimensionalise (pvSimPCR.py:327-331), one column per lane, then broadcast
+    double mpl = 0.0;
+    if (lane < TRPL_NPAR) mpl = a.x[s * a.ldx + lane] * cv.scales[lane];
+    const double N0 = __shfl_sync(FULL, mpl, 0), P0 = __shfl_sync(FULL, mpl, 1);
+    const double DN = __shfl_sync(FULL, mpl, 2), DP = __shfl_sync(FULL, mpl, 3);
+    const double rate = __shfl_sync(FULL, mpl, 4);
+    const double sr0 = __shfl_sync(FULL, mpl, 5), srL = __shfl_sync(FULL, mpl, 6);
+    const double CN = __shfl_sync(FULL, mpl, 7), CP = __shfl_sync(FULL, mpl, 8);
+    const double tauN = __shfl_sync(FULL, mpl, 9), tauP = __shfl_sync(FULL, mpl, 10);
+    const double Lam = __shfl_sync(FULL, mpl, 11);
+    const double N0P0 = N0 * P0;
+    const double hDN = 0.5 * DN, hDP = 0.5 * DP;
+    const double CN_N0P0 = CN * N0P0, CP_N0P0 = CP * N0P0;
+    const double LamDP = Lam * DP, LamDN = Lam * DN, hLamDP = 0.5 * LamDP, hLamDN = 0.5 * LamDN;
+    const double TOL = a.TOL;
+    const double mag = (a.mag_col >= 0) ? a.x[s * a.ldx + a.mag_col] : 0.0;
+
+    // ---- geometry of this lane
+    const int last_lane = (L - 1) / M;         // lane owning node L-1 (at j = M-1 since L % M == 0)
+    bool ev[M + 1];                            // edge m = M*g + j is an interior edge (1..L-1)
+#pragma unroll
+    for (int j = 0; j <= M; j++) {
+        const int m = M * g + j;
+        // exact-fit grids (L == M*G): only edge 0 (first lane) and edge L (last lane) are
+        // boundaries, so the selects on the inner edges fold away at compile time
+        ev[j] = PAD ? ((m >= 1) && (m <= L - 1)) : (j == 0 ? (g != 0) : (j == M ? (g != G - 1) : true));
+    }
+    bool nv[M];                                // node n = M*g + j exists
+#pragma unroll
+    for (int j = 0; j < M; j++) nv[j] = PAD ? (M * g + j < L) : true;
+    // surface rows: lane 0 applies the front surface to j=0, last_lane the back surface to j=M-1
+    const bool is_first = (g == 0), is_last = (g == last_lane);
+    const double srf = is_first ? sr0 : (is_last ? srL : 0.0);
+
+    // ---- initial state (pvSimPCR.py:339-362): N = N0 + dN, P = P0 + dN, E = 0
+    double N[M], P[M], E[M];
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+        const int n = M * g + j;
+        double dn = 0.0;
+        if (n < L) dn = cv.init[n] * cv.init_mul;
+        N[j] = nv[j] ? N0 + dn : 0.0;
+        P[j] = nv[j] ? P0 + dn : 0.0;
+        E[j] = 0.0;
+    }
+    Ring<M> ring;
+    ring.base = ring_warp + ((M == 1) ? lane : 2 * lane);
+    {
+        double z[M];
+#pragma unroll
+        for (int j = 0; j < M; j++) z[j] = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < 4; sl++)
+#pragma unroll
+            for (int f = 0; f < 3; f++) ring.store(sl, f, z);
+    }
+    if (io_warp && lane < TRPL_MAX_EXP) {
+        ws->sse[lane] = 0.0;
+        ws->pos[lane] = 0;
+    }
+    __syncwarp();
+
+    // neighbour values carried across iterations and steps
+    double Nl, Nr, Pl, Pr;
+    {
+        double mine[2] = {N[M - 1], P[M - 1]}, vm[2], vp[2];
+        cm.template xchg<2, true, false>(mine, 1, 1, vm, vp);
+        Nl = vm[0]; Pl = vm[1];
+        double mine2[2] = {N[0], P[0]};
+        cm.template xchg<2, false, true>(mine2, 1, 1, vm, vp);
+        Nr = vp[0]; Pr = vp[1];
+    }
+    double En = 0.0;   // E on edge M*g + M (owned by the next lane)
+
+    const double mLN0P0 = -(double)L * N0P0;   // pvSimPCR.py:278
+    const int t_last = cv.t_last;
+    const int plT = a.plT;
+    const int n_pl = t_last / plT + 1;
+    double keep = 0.0;          // PL sample staged in this lane
+    double lp_carry = 0.0;      // log PL of the sample preceding the current block of 32
+    double pl0 = 1.0;           // PL(t=0) for self-normalisation
+    long long iters_total = 0;
+    int status = 0;
+    int pl_idx = 0;             // index of the next PL sample
+    int t_next_pl = 0;
+
+    // consume a block of `cnt` staged PL samples starting at index idx0
+    auto flush = [&](const int idx0, const int cnt) {
+        double val;
+        if (emu32) {
+            float f = (float)keep;             // value rounded on store into the f32 buffer
+            f = f / (float)cv.redim;           // plI_main /= dx**2*dt in float32
+            val = (double)f;
+        } else {
+            val = keep / cv.redim;
+        }
+        if (cv.pl_out != nullptr && lane < cnt) {
+            if (a.pl_dtype == TRPL_F32)
+                reinterpret_cast<float *>(cv.pl_out)[s * a.pl_stride + idx0 + lane] = (float)val;
+            else
+                reinterpret_cast<double *>(cv.pl_out)[s * a.pl_stride + idx0 + lane] = val;
+        }
+        if (a.E == 0) return;
+        if (flags & TRPL_F_SELF_NORMALIZE) {
+            if (idx0 == 0) pl0 = __shfl_sync(FULL, val, 0);
+            val = emu32 ? (double)((float)val / (float)pl0) : val / pl0;
+        }
+        double lp = val;
+        if (flags & TRPL_F_LOG_PL) {
+            if (emu32) {
+                float f = (float)val;
+                if ((double)f < DBL_MIN) f = 0.0f;   // (float)sys.float_info.min == 0  (probs.py:72-73)
+                lp = (double)log10f(f);
+            } else {
+                lp = log10(val < DBL_MIN ? DBL_MIN : val);
+            }
+        }
+        for (int e = 0; e < a.E; e++) {
+            const ObsDev &ob = cv.obs[e];
+            int pos = ws->pos[e];
+            double acc = 0.0;
+            for (;;) {
+                const int i = pos + lane;
+                const int h = (i < ob.n) ? ob.hi[i] : INT_MAX;
+                const bool mine = h < idx0 + cnt;
+                const unsigned bm = __ballot_sync(FULL, mine);
+                if (bm == 0u) break;
+                const int shi = mine ? h - idx0 : 0;       // 0..cnt-1
+                const int slo = shi - 1;                   // -1..cnt-2
+                const double y_hi = __shfl_sync(FULL, lp, shi & 31);
+                double y_lo = __shfl_sync(FULL, lp, slo & 31);
+                if (slo < 0) y_lo = lp_carry;
+                double sq = 0.0;
+                if (mine) {
+                    // scipy interp1d._call_linear: w_hi*y_hi + w_lo*y_lo, no contraction
+                    const double yi = __dadd_rn(__dmul_rn(ob.whi[i], y_hi), __dmul_rn(ob.wlo[i], y_lo));
+                    double err = yi + mag;                  // probs.py:33-38
+                    err -= ob.val[i];
+                    sq = err * err;
+                }
+                acc += warp_sum(sq);
+                const int took = __popc(bm);
+                pos += took;
+                if (took < 32) break;
+            }
+            if (lane == 0) {
+                ws->pos[e] = pos;
+                ws->sse[e] += acc;
+            }
+        }
+        lp_carry = __shfl_sync(FULL, lp, cnt - 1);
+        __syncwarp();
+    };
+
+    // =========================================================================================
+    // time loop (pvSimPCR.py:237-293): t = 0 .. t_last, PL(t) emitted from the state at time t
+    // =========================================================================================
+    bool failed = false;
+    int t;
+    for (t = 0; t <= t_last; t++) {
+        // ---- PL(t) = rate * (sum_n N*P - L*N0*P0)                          (pvSimPCR.py:276-281)
+        bool emitted = false;
+        if (t == t_next_pl) {
+            emitted = true;
+            double part = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; j++) part = fma(N[j], P[j], part);
+            const double tot = cm.sum(part);
+            const double plraw = rate * (tot + mLN0P0);
+            if (lane == (pl_idx & 31)) keep = plraw;
+            t_next_pl += plT;
+            pl_idx++;
+        }
+
+        // ---- BDF coefficients, order ramp 1..5                            (pvSimPCR.py:241-250)
+        double a0, a1, a2, a3, a4, a5;
+        {
+            int order = t + 1;
+            if (order > 5) order = 5;
+            if (order > a.max_order) order = a.max_order;
+            a2 = a3 = a4 = a5 = 0.0;
+            if (order == 1) { a0 = 1.0; a1 = -1.0; }
+            else if (order == 2) { a0 = 1.5; a1 = -2.0; a2 = 0.5; }
+            else if (order == 3) { a0 = 11.0 / 6; a1 = -3.0; a2 = 1.5; a3 = -1.0 / 3; }
+            else if (order == 4) { a0 = 25.0 / 12; a1 = -4.0; a2 = 3.0; a3 = -4.0 / 3; a4 = 0.25; }
+            else { a0 = 137.0 / 60; a1 = -5.0; a2 = 5.0; a3 = -10.0 / 3; a4 = 1.25; a5 = -0.2; }
+        }
+
+        // ---- history sums bU = a1 U(t) + a2 U(t-1) + ... + a5 U(t-4)       (pvSimPCR.py:133-135)
+        double bN[M], bP[M], bE[M];
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            bN[j] = a1 * N[j];
+            bP[j] = a1 * P[j];
+            bE[j] = a1 * E[j];
+        }
+        {
+            const double ac[4] = {a2, a3, a4, a5};
+#pragma unroll
+            for (int i = 1; i <= 4; i++) {
+                const int slot = (t - i) & 3;
+                double h[M];
+                ring.load(slot, 0, h);
+#pragma unroll
+                for (int j = 0; j < M; j++) bN[j] = fma(ac[i - 1], h[j], bN[j]);
+                ring.load(slot, 1, h);
+#pragma unroll
+                for (int j = 0; j < M; j++) bP[j] = fma(ac[i - 1], h[j], bP[j]);
+                ring.load(slot, 2, h);
+#pragma unroll
+                for (int j = 0; j < M; j++) bE[j] = fma(ac[i - 1], h[j], bE[j]);
+            }
+            const int slot = t & 3;    // level t replaces level t-4
+            ring.store(slot, 0, N);
+            ring.store(slot, 1, P);
+            ring.store(slot, 2, E);
+        }
+
+        // ---- Newton / Gauss-Seidel iteration                              (pvSimPCR.py:147-216)
+        int it = 0;
+        bool nonfinite = false;
+        for (;;) {
+            double l[M], d[M], u[M], b[M];
+            double zN = 0.0, zP = 0.0;    // sum(|residual| - TOL*|b|): err < TOL  <=>  z < 0
+            bool converged_now = false, nonfinite_now = false;
+
+            // ======== N system (P, E frozen) ========
+            {
+                double cu[M + 1], cl[M + 1];   // edge coefficients: cu[m] = upper of row m-1, cl[m] = lower of row m
+#pragma unroll
+                for (int j = 0; j <= M; j++) {
+                    const double Ej = (j < M) ? E[j] : En;
+                    cu[j] = sel(ev[j], fma(-hDN, Ej, -DN), 0.0);     // DN*(-E/2 - 1)
+                    cl[j] = sel(ev[j], fma(hDN, Ej, -DN), 0.0);      // DN*(+E/2 - 1)
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const double Nj = N[j], Pj = P[j];
+                    const double tp = fma(Nj, tauP, Pj * tauN);
+                    const double NP = Nj * Pj;
+                    const double npp = NP - N0P0;
+                    const double r = rcp64(tp);
+                    const double q = fma(-tauP, npp, Pj * tp);
+                    const double srh = (q * r) * r;
+                    const double cnN = CN * Nj;
+                    const double aug = fma(Pj, fma(CP, Pj, cnN + cnN), -CN_N0P0);   // CN*N*P + CP*P^2 + CN*np
+                    const double nds = fma(rate, Pj, srh) + aug;             // = -ds
+                    l[j] = cl[j];
+                    u[j] = cu[j + 1];
+                    d[j] = ((a0 - cu[j]) - cl[j + 1]) + nds;
+                    const double g = fma(CP, Pj, cnN) + (rate + r);
+                    b[j] = fma(nds, Nj, -fma(g, npp, bN[j]));
+                }
+                // surface recombination rows                                 (pvSimPCR.py:164-170)
+                {
+                    const double Ns = is_first ? N[0] : N[M - 1];
+                    const double Ps = is_first ? P[0] : P[M - 1];
+                    const double rs = rcp64(Ns + Ps);
+                    const double nd = (srf * fma(Ps, Ps, N0P0)) * (rs * rs);        // = -ds0
+                    const double db = fma(-nd, Ns, (srf * fma(Ns, Ps, -N0P0)) * rs);
+                    d[0] += is_first ? nd : 0.0;
+                    b[0] -= is_first ? db : 0.0;
+                    d[M - 1] += is_last ? nd : 0.0;
+                    b[M - 1] -= is_last ? db : 0.0;
+                }
+                if (PAD) {
+#pragma unroll
+                    for (int j = 0; j < M; j++) {
+                        l[j] = sel(nv[j], l[j], 0.0);
+                        u[j] = sel(nv[j], u[j], 0.0);
+                        d[j] = sel(nv[j], d[j], 1.0);
+                        b[j] = sel(nv[j], b[j], 0.0);
+                    }
+                }
+                // L1 residual of the current iterate                         (pvSimPCR.py:172, :14-40)
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const double xm = (j == 0) ? Nl : N[j - 1];
+                    const double xp = (j == M - 1) ? Nr : N[j + 1];
+                    const double res = fma(l[j], xm, fma(d[j], N[j], fma(u[j], xp, -b[j])));
+                    zN = fma(-TOL, fabs(b[j]), zN + fabs(res));
+                }
+                Nl = tridiag_solve<M, W>(l, d, u, b, N, cm);
+                Nr = cm.from_next(N[0]);
+            }
+
+            // ======== P system (new N) ========
+            {
+                double cu[M + 1], cl[M + 1];
+#pragma unroll
+                for (int j = 0; j <= M; j++) {
+                    const double Ej = (j < M) ? E[j] : En;
+                    cu[j] = sel(ev[j], fma(hDP, Ej, -DP), 0.0);      // DP*(+E/2 - 1)
+                    cl[j] = sel(ev[j], fma(-hDP, Ej, -DP), 0.0);     // DP*(-E/2 - 1)
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const double Nj = N[j], Pj = P[j];
+                    const double tp = fma(Nj, tauP, Pj * tauN);
+                    const double NP = Nj * Pj;
+                    const double npp = NP - N0P0;
+                    const double r = rcp64(tp);
+                    const double q = fma(-tauN, npp, Nj * tp);
+                    const double srh = (q * r) * r;
+                    const double cpP = CP * Pj;
+                    const double aug = fma(Nj, fma(CN, Nj, cpP + cpP), -CP_N0P0);   // CP*N*P + CN*N^2 + CP*np
+                    const double nds = fma(rate, Nj, srh) + aug;
+                    l[j] = cl[j];
+                    u[j] = cu[j + 1];
+                    d[j] = ((a0 - cu[j]) - cl[j + 1]) + nds;
+                    const double g = fma(CN, Nj, cpP) + (rate + r);
+                    b[j] = fma(nds, Pj, -fma(g, npp, bP[j]));
+                }
+                {
+                    const double Ns = is_first ? N[0] : N[M - 1];
+                    const double Ps = is_first ? P[0] : P[M - 1];
+                    const double rs = rcp64(Ns + Ps);
+                    const double nd = (srf * fma(Ns, Ns, N0P0)) * (rs * rs);
+                    const double db = fma(-nd, Ps, (srf * fma(Ns, Ps, -N0P0)) * rs);
+                    d[0] += is_first ? nd : 0.0;
+                    b[0] -= is_first ? db : 0.0;
+                    d[M - 1] += is_last ? nd : 0.0;
+                    b[M - 1] -= is_last ? db : 0.0;
+                }
+                if (PAD) {
+#pragma unroll
+                    for (int j = 0; j < M; j++) {
+                        l[j] = sel(nv[j], l[j], 0.0);
+                        u[j] = sel(nv[j], u[j], 0.0);
+                        d[j] = sel(nv[j], d[j], 1.0);
+                        b[j] = sel(nv[j], b[j], 0.0);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const double xm = (j == 0) ? Pl : P[j - 1];
+                    const double xp = (j == M - 1) ? Pr : P[j + 1];
+                    const double res = fma(l[j], xm, fma(d[j], P[j], fma(u[j], xp, -b[j])));
+                    zP = fma(-TOL, fabs(b[j]), zP + fabs(res));
+                }
+                // ---- stop decision for THIS iteration (pvSimPCR.py:213-216): both L1 residuals are
+                // known here, before the P solve; reducing them now lets the shuffle chain overlap
+                // the solve.
+                cm.stop_rule(zN, zP, converged_now, nonfinite_now);
+                Pl = tridiag_solve<M, W>(l, d, u, b, P, cm);
+                Pr = cm.from_next(P[0]);
+            }
+
+            // ======== E update on interior edges                           (pvSimPCR.py:205-209)
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                const double Nm = (j == 0) ? Nl : N[j - 1];
+                const double Pm = (j == 0) ? Pl : P[j - 1];
+                const double den = fma(hLamDP, P[j] + Pm, fma(hLamDN, N[j] + Nm, a0));
+                const double num = fma(LamDP, P[j] - Pm, fma(-LamDN, N[j] - Nm, -bE[j]));
+                E[j] = sel(ev[j], num * rcp64(den), 0.0);
+            }
+            En = cm.from_next(E[0]);
+
+            // ======== stop rule (pvSimPCR.py:213-216): decided by the flags computed before the P solve
+            it++;
+            if (nonfinite_now) { nonfinite = true; break; }
+            if (converged_now) break;
+            if (it >= a.max_iter) break;
+        }
+        iters_total += it;
+        if (nonfinite || it >= a.max_iter) {                 // pvSimPCR.py:269-274
+            status |= nonfinite ? TRPL_ST_NONFINITE : TRPL_ST_NOCONV;
+            failed = true;
+            // the reference stops before emitting PL(t): un-count the sample staged for this step
+            if (emitted) pl_idx--;
+            break;
+        }
+        if (io_warp && emitted && (pl_idx & 31) == 0) flush(pl_idx - 32, 32);
+    }
+
+    // ---- tail: partially filled block; after a failure everything from pl_idx on is NaN
+    if (io_warp && (pl_idx & 31)) flush(pl_idx & ~31, pl_idx & 31);
+    if (io_warp && failed && cv.pl_out != nullptr) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int i = pl_idx + lane; i < n_pl; i += 32) {
+            if (a.pl_dtype == TRPL_F32)
+                reinterpret_cast<float *>(cv.pl_out)[s * a.pl_stride + i] = (float)qnan;
+            else
+                reinterpret_cast<double *>(cv.pl_out)[s * a.pl_stride + i] = qnan;
+        }
+    }
+
+    // ---- results
+    __syncwarp();
+    if (io_warp && lane == 0) {
+        const long long cs = (long long)c * a.S + s;
+        if (a.status) a.status[cs] = status;
+        if (a.iters) a.iters[cs] = iters_total;
+    }
+    if (io_warp && a.sse != nullptr && lane < a.E) {
+        double v = ws->sse[lane];
+        if (failed && ws->pos[lane] < cv.obs[lane].n) v = __longlong_as_double(0x7ff8000000000000LL);
+        a.sse[((long long)lane * a.C + c) * a.S + s] = v;
+    }
+    __syncwarp();
+}
+
+template <int M, bool PAD>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, TRPL_MIN_CTAS)
+trpl_sim_kernel(const __grid_constant__ KArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ WarpScratch scratch[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32);
+    const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
+    Comm<1> cm;
+    cm.g = lane; cm.xb = nullptr; cm.red = nullptr; cm.phase = 0; cm.rphase = 0;
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.counter, 1ULL);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= total) break;
+        const long long s = (long long)(item / (unsigned)a.C);
+        const int c = (int)(item % (unsigned)a.C);
+        run_sim<M, PAD, 1>(a, c, s, ring_warp, &scratch[warp], lane, cm);
+    }
+}
+
+// Fine grids: one CTA of W warps per simulation, 4 nodes per lane (L <= 128*W).
+template <int W>
+__global__ void __launch_bounds__(W * 32, 16 / W)
+trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
+{
+    constexpr int M = 4;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ WarpScratch scratch;
+    __shared__ unsigned long long next_item;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32);
+    Comm<W> cm;
+    cm.g = threadIdx.x;
+    cm.xb = smem + (size_t)W * (4 * 3 * M * 32);
+    cm.red = cm.xb + 2 * 3 * 32 * W;
+    cm.phase = 0; cm.rphase = 0;
+    const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_item = atomicAdd(a.counter, 1ULL);
+        __syncthreads();
+        const unsigned long long item = next_item;
+        if (item >= total) break;
+        const long long s = (long long)(item / (unsigned)a.C);
+        const int c = (int)(item % (unsigned)a.C);
+        run_sim<M, true, W>(a, c, s, ring_warp, &scratch, lane, cm);
+    }
+}
+
+
+}  // namespace trpl

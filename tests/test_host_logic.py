@@ -31,7 +31,7 @@ def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "bayesian_inference_trpl_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), f
 
