@@ -50,6 +50,7 @@ struct KArgs {
     unsigned long long *counter; // work-item counter (zeroed by the host)
     int mag_col;                 // < 0: no magnitude offset
     int C, E, L, plT, max_iter, max_order, flags, pl_dtype;
+    int curve_order[TRPL_MAX_CURVES];   // curves sorted by decreasing work (longest first)
     CurveDev curves[TRPL_MAX_CURVES];
 };
 

@@ -151,6 +151,12 @@ int launch_sims(KArgs &ka, const Cfg &cfg, int device, cudaStream_t st)
     kern_t k; size_t smem; int nb, nsm;
     int rc = kernel_geometry(device, cfg, &k, &smem, &nb, &nsm);
     if (rc) return rc;
+    // longest-processing-time-first order of the curves (insertion sort, C <= 8)
+    for (int c = 0; c < ka.C; c++) ka.curve_order[c] = c;
+    for (int i = 1; i < ka.C; i++)
+        for (int j = i; j > 0 && ka.curves[ka.curve_order[j]].t_last > ka.curves[ka.curve_order[j - 1]].t_last; j--) {
+            const int t = ka.curve_order[j]; ka.curve_order[j] = ka.curve_order[j - 1]; ka.curve_order[j - 1] = t;
+        }
     unsigned long long *counter = nullptr;
     CK(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));

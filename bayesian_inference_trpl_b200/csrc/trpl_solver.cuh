@@ -679,8 +679,9 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
         if (lane == 0) item = atomicAdd(a.counter, 1ULL);
         item = __shfl_sync(FULL, item, 0);
         if (item >= total) break;
-        const long long s = (long long)(item / (unsigned)a.C);
-        const int c = (int)(item % (unsigned)a.C);
+        // items are issued curve-major, longest curve first, so short ones fill the tail of the launch
+        const int c = a.curve_order[(int)(item / (unsigned long long)a.S)];
+        const long long s = (long long)(item % (unsigned long long)a.S);
         run_sim<M, PAD, 1>(a, c, s, ring_warp, &scratch[warp], lane, cm);
     }
 }
@@ -708,8 +709,8 @@ trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
         __syncthreads();
         const unsigned long long item = next_item;
         if (item >= total) break;
-        const long long s = (long long)(item / (unsigned)a.C);
-        const int c = (int)(item % (unsigned)a.C);
+        const int c = a.curve_order[(int)(item / (unsigned long long)a.S)];
+        const long long s = (long long)(item % (unsigned long long)a.S);
         run_sim<M, true, W>(a, c, s, ring_warp, &scratch, lane, cm);
     }
 }
