@@ -593,3 +593,66 @@ def test_degenerate_parameters_match_oracle(trpl, oracle):
     np.testing.assert_array_equal(st, ref["status"])
     assert (st == 0).all()
     _assert_pl_close(pl, ref["pl"], X[:, :12], simPar, rtol=1e-8)
+
+
+_NCCL_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import bayesian_inference_trpl_b200 as trpl
+from bayesian_inference_trpl_b200 import distributed as D
+from helpers import TRUTH, UC, MINX, MAXX, DO_LOG, power_scan_excitations
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+L, T = 128, 200
+simPar = [2000.0, 0.025 * T, L, T, 1, (0,), 7, 10000]
+inis = power_scan_excitations()
+grid = np.linspace(0, simPar[1], T + 1)
+e_data = [([grid.copy()] * 3, [np.linspace(-6.5, -7.5, T + 1)] * 3, [np.full(T + 1, .1)] * 3)]
+flags = {"load_PL_from_file": False, "override_equal_auger": False, "override_equal_mu": False,
+         "override_equal_s": False, "log_pl": True, "self_normalize": False, "random_sample": True, "num_points": 37}
+lo, hi = MINX * UC, MAXX * UC
+lo[2:4] = 0.5 * UC[2:4]
+def run(num_gpus):
+    gi = {"sims_per_gpu": 5, "num_gpus": num_gpus}
+    trpl.bayes_validate.connect_to_gpu(gi)
+    np.random.seed(42)
+    return trpl.bayeslib.bayes(trpl.pvSim, np.array([0]), None, lo, hi, DO_LOG, inis, list(simPar), e_data, flags, gi)
+N, P, X = run(world)                       # block-cyclic share of this rank (RANK from torchrun)
+full = D.merge_block_cyclic(P).cpu().numpy()
+os.environ.pop("RANK"); N1, P1, X1 = run(1); os.environ["RANK"] = str(rank)   # whole table on one GPU
+assert np.array_equal(X, X1)
+assert np.allclose(full, P1, rtol=1e-12, atol=0), np.abs(full - P1).max()
+own = np.zeros(37, bool)
+for b in range(rank * 5, 37, world * 5): own[b:b + 5] = True
+assert (P[0][~own] == 0).all() and (P[0][own] != 0).all()
+# contiguous shards + NCCL gather + global log-sum-exp
+a, b = D.shard_bounds(37, rank, world)
+loc = torch.from_numpy(P1[:, a:b].copy()).cuda()
+got = D.gather_rows(loc, 37).cpu().numpy()
+assert np.array_equal(got, P1)
+lse = D.global_logsumexp(trpl.engine.lse_partial(loc[0].contiguous()))
+m = P1[0].max(); ref = m + np.log(np.exp(P1[0] - m).sum())
+assert abs(float(lse) - ref) < 1e-10 * abs(ref)
+w = trpl.posterior.normalize(loc[0].contiguous())
+tot = w.sum(); dist.all_reduce(tot)
+assert abs(float(tot) - 1.0) < 1e-12
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_gpu_nccl_sharding_and_merge(trpl, tmp_path):
+    """Two ranks on two GPUs: block-cyclic bayes() shares merged over NCCL equal the one-GPU table;
+    all-gather of contiguous shards and the global log-sum-exp (skipped on a one-GPU box)."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "nccl_worker.py"
+    script.write_text(_NCCL_WORKER % {"root": root})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
