@@ -25,6 +25,7 @@
 // All arithmetic is FP64 like the reference (pvSimPCR.py:11,113-125).  Divisions are replaced by
 // a Newton-refined reciprocal (MUFU.RCP64H seed), accurate to <= 1 ulp; see DESIGN.md.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "trpl_common.cuh"
@@ -76,11 +77,13 @@ int pick_cfg(int L, Cfg *cfg)
         }
         if (L < 128) return TRPL_EUNSUPPORTED;    // odd small grids: need L % M == 0
     }
-    // fine grids: 4 nodes per lane, W warps per simulation
+    // fine grids: one CTA of W warps per simulation; 8 nodes per lane when L allows (fewer interface
+    // unknowns, less PCR work per node), else 4
     if (L % 4 != 0 || L > 128 * 16) return TRPL_EUNSUPPORTED;
+    const int M = (L % 8 == 0 && getenv("TRPL_FINE_M4") == nullptr) ? 8 : 4;
     int W = 2;
-    while (128 * W < L) W <<= 1;
-    cfg->M = 4; cfg->pad = true; cfg->W = W;
+    while (32 * M * W < L) W <<= 1;
+    cfg->M = M; cfg->pad = true; cfg->W = W;
     return TRPL_OK;
 }
 
@@ -88,11 +91,18 @@ typedef void (*kern_t)(const KArgs);
 kern_t pick_kernel(const Cfg &c)
 {
     if (c.W > 1) {
+        if (c.M == 8) {
+            switch (c.W) {
+            case 2: return trpl_sim_cta_kernel<2, 8>;
+            case 4: return trpl_sim_cta_kernel<4, 8>;
+            default: return trpl_sim_cta_kernel<8, 8>;
+            }
+        }
         switch (c.W) {
-        case 2: return trpl_sim_cta_kernel<2>;
-        case 4: return trpl_sim_cta_kernel<4>;
-        case 8: return trpl_sim_cta_kernel<8>;
-        default: return trpl_sim_cta_kernel<16>;
+        case 2: return trpl_sim_cta_kernel<2, 4>;
+        case 4: return trpl_sim_cta_kernel<4, 4>;
+        case 8: return trpl_sim_cta_kernel<8, 4>;
+        default: return trpl_sim_cta_kernel<16, 4>;
         }
     }
     switch (c.M) {

@@ -686,12 +686,11 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
     }
 }
 
-// Fine grids: one CTA of W warps per simulation, 4 nodes per lane (L <= 128*W).
-template <int W>
-__global__ void __launch_bounds__(W * 32, 16 / W)
+// Fine grids: one CTA of W warps per simulation, M nodes per lane (L <= 32*M*W).
+template <int W, int M>
+__global__ void __launch_bounds__(W * 32, (M == 4) ? 16 / W : 1)
 trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
 {
-    constexpr int M = 4;
     extern __shared__ __align__(16) double smem[];
     __shared__ WarpScratch scratch;
     __shared__ unsigned long long next_item;
