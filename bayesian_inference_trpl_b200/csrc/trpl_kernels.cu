@@ -1,5 +1,8 @@
 // trpl_kernels.cu -- sm_100a kernels + C ABI of libtrpl_b200.so (see include/trpl_b200.h).
 //
+// Files: trpl_solver.cuh (hot path), trpl_aux_kernels.cuh (small kernels), trpl_common.cuh (argument
+// structs, helpers), this file (host side + C ABI).
+//
 // Hot path replaced: pvSimPCR.py:14-401 (tEvol/iterate/pcreduce/norm2 + pvSim host driver) and
 // probs.py:20-85 (kernel_lnP, log_kernel), plus the glue bayeslib.simulate runs between them
 // (bayeslib.py:150-196).  Written from scratch for B200; nothing here is a translation of the
@@ -14,7 +17,7 @@
 //     per lane eliminated in place) + a 32-lane parallel cyclic reduction on the interface
 //     unknowns done with warp shuffles (5 normalised stages instead of the reference's
 //     log2(L)-1 shared-memory stages over all L rows);
-//   * the L1 residual norms of both species are reduced together with a 4-value butterfly;
+//   * the stop rule of both species is reduced together with one 2-value butterfly, division-free;
 //   * PL(t) is a warp reduction; 32 consecutive PL values are staged one per lane and then
 //     consumed together: written with one coalesced store (trpl_solve_pl) and/or turned into
 //     log10, time-interpolated onto the observation times and accumulated into the squared

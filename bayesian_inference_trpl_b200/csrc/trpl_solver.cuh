@@ -1,6 +1,6 @@
 // trpl_solver.cuh -- the forward-model + fused-likelihood kernels (the hot path):
 // Comm<W> (lane communication policy), tridiag_solve, Ring, run_sim, trpl_sim_kernel<M,PAD>,
-// trpl_sim_cta_kernel<W>.  Replaces pvSimPCR.py:14-293 and bayeslib.py:150-196.
+// trpl_sim_cta_kernel<W,M>.  Replaces pvSimPCR.py:14-293 and bayeslib.py:150-196.
 #pragma once
 #include "trpl_common.cuh"
 
@@ -9,7 +9,7 @@ namespace trpl {
 // ---------------------------------------------------------------------------------------------
 // Communication among the lanes that share one simulation.  W = warps per simulation.
 //   W == 1: warp shuffles / votes only (the production path for L <= 256).
-//   W  > 1: one CTA of W warps per simulation (fine grids, L up to 128*W); values travel through a
+//   W  > 1: one CTA of W warps per simulation (fine grids, L up to 32*M*W); values travel through a
 //           ping-pong exchange buffer in shared memory, one __syncthreads per exchange.  Every
 //           thread of the CTA executes the same sequence of exchanges.
 // g = index of this lane among the 32*W lanes of the simulation.
@@ -65,11 +65,6 @@ struct Comm {
         double a[1] = {v}, m[1], p_[1];
         xchg<1, false, true>(a, 1, 1, m, p_);
         return p_[0];
-    }
-    __device__ __forceinline__ bool all(const bool pred)
-    {
-        if constexpr (W == 1) return __all_sync(FULL, pred);
-        else return __syncthreads_and(pred) != 0;
     }
     __device__ __forceinline__ double sum(double v)                 // total over the simulation
     {

@@ -80,24 +80,6 @@ def scales(length, time, L, T):
     return s, dx.value, dt.value
 
 
-def init_points(iniPar, length, L, init_mode="points"):
-    """Initial excess-carrier profile in physical units (pvSimPCR.py:347-356).
-
-    "exp": iniPar=(a, l) -> a*exp(-x/l) at the cell centres; evaluated with numpy exactly as
-    the reference does (in grid units, then mapped back) so that exp() rounding is shared.
-    """
-    if init_mode == "points":
-        return np.ascontiguousarray(iniPar, dtype=np.float64)
-    if init_mode == "exp":
-        dx = length / L
-        a, l = iniPar
-        a = a * dx ** 3
-        l = l / dx
-        x = np.arange(L) + 0.5
-        return np.ascontiguousarray((a * np.exp(-x / l)) / dx ** 3)
-    raise ValueError("init_mode must be 'points' or 'exp'")
-
-
 def solve(matPar, simPar, iniPar, init_mode="points", solver="pcr", max_order=5, nthreads=0,
           return_state=False, raw=False, simulator_pow=False):
     """Oracle of pvSimPCR.pvSim (pvSimPCR.py:309-401) for ONE curve.
