@@ -173,11 +173,13 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
     for (int rf = 1; rf < 32 * W; rf <<= 1) {
         // Off-diagonals shrink quadratically per stage; once every |L|,|U| of the simulation is
         // below 2^-70 the remaining stages cannot change D = 1 or B in the last bit: stop.
+        // (Not tested before the first three stages: a coupling that small after two stages means
+        // an initial one below 2^-17, i.e. practically no transport; those cases just run 3 stages.)
         const int hl = __double2hiint(Lr) & 0x7fffffff, hu = __double2hiint(Ur) & 0x7fffffff;
-        const bool busy = (rf < 2) || (max(hl, hu) >= ((1023 - 70) << 20));
+        const bool busy = (rf < 8) || (max(hl, hu) >= ((1023 - 70) << 20));
         double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
         if constexpr (W == 1) {
-            if (rf >= 2 && !__any_sync(FULL, busy)) break;
+            if (rf >= 8 && !__any_sync(FULL, busy)) break;
             cm.template xchg<3, true, true>(mine, rf, rf, vm, vp);
         } else {
             if (!cm.template xchg<3, true, true>(mine, rf, rf, vm, vp, busy)) break;
@@ -430,6 +432,9 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
         }
 
         // ---- BDF coefficients, order ramp 1..5                            (pvSimPCR.py:241-250)
+        // (re-selected every step on purpose: as step-local values they stay in uniform registers;
+        // hoisted out of the loop they become loop-carried vector registers and 29 more DFMAs per
+        // iteration turn into the 3-cycle three-register kind)
         double a0, a1, a2, a3, a4, a5;
         {
             int order = t + 1;
