@@ -656,3 +656,23 @@ def test_two_gpu_nccl_sharding_and_merge(trpl, tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_fused_path_marks_nonconverged_samples(trpl, oracle):
+    """max_iter too small for some samples: their lnL is NaN and status bit0 is set, the others
+    are unaffected (the reference would abort the whole launch, pvSimPCR.py:269-274)."""
+    L, T, length = 128, 120, 2000.0
+    simPar = [length, 0.025 * T, L, T, 1, (0,), 7, 80]           # too few for the first steps of some samples
+    inis = power_scan_excitations()[0:2]
+    X = prior_samples(12, seed=123)
+    grid = np.linspace(0, simPar[1], T + 1)
+    e_data = [([grid.copy()] * 2, [np.full(T + 1, -7.0)] * 2, [np.full(T + 1, 0.1)] * 2)]
+    ref = oracle.loglik(X, simPar, inis, e_data, solver="pcr")
+    prob = trpl.engine.Problem(simPar, inis, e_data, device=0)
+    lnl, status, _ = trpl.engine.solve_loglik(torch.from_numpy(X).cuda(), prob)
+    got, st = lnl.cpu().numpy()[0], status.cpu().numpy()
+    assert (st != 0).any() and (st == 0).any()
+    np.testing.assert_array_equal(np.isnan(got), st != 0)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref[0]))
+    ok = st == 0
+    np.testing.assert_allclose(got[ok], ref[0][ok], rtol=1e-6)
