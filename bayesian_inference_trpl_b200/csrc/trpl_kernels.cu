@@ -72,20 +72,19 @@ int pick_cfg(int L, Cfg *cfg)
 {
     if (L < 2) return TRPL_EINVAL;
     if (L <= 256) {
+        // one warp per simulation, M nodes per lane; grids that do not fill 32*M nodes are padded
         int M = 1;
         while (32 * M < L) M <<= 1;
-        if (L % M == 0 && L >= 2 * M) {
-            cfg->M = M; cfg->pad = (L != 32 * M); cfg->W = 1;
-            return TRPL_OK;
-        }
-        if (L < 128) return TRPL_EUNSUPPORTED;    // odd small grids: need L % M == 0
+        cfg->M = M; cfg->pad = (L != 32 * M); cfg->W = 1;
+        return TRPL_OK;
     }
-    // fine grids: one CTA of W warps per simulation; 8 nodes per lane when L allows (fewer interface
-    // unknowns, less PCR work per node), else 4
-    if (L % 4 != 0 || L > 128 * 16) return TRPL_EUNSUPPORTED;
-    const int M = (L % 8 == 0 && getenv("TRPL_FINE_M4") == nullptr) ? 8 : 4;
+    // fine grids: one CTA of W warps per simulation; 8 nodes per lane (fewer interface unknowns,
+    // less PCR work per node than 4; TRPL_FINE_M4=1 selects 4 for A/B tests)
+    if (L > 256 * 8) return TRPL_EUNSUPPORTED;
+    const int M = (getenv("TRPL_FINE_M4") == nullptr) ? 8 : 4;
     int W = 2;
     while (32 * M * W < L) W <<= 1;
+    if (W > 16) return TRPL_EUNSUPPORTED;
     cfg->M = M; cfg->pad = true; cfg->W = W;
     return TRPL_OK;
 }
@@ -202,9 +201,7 @@ const char *trpl_error_string(int code)
     switch (code) {
     case TRPL_OK: return "ok";
     case TRPL_EINVAL: return "invalid argument";
-    case TRPL_EUNSUPPORTED: return "unsupported shape (need L <= 256 with L = M*g, M in {1,2,4,8}, "
-                                   "2 <= g <= 32, or L <= 2048 with L % 4 == 0; curves <= 8, "
-                                   "observation files <= 4)";
+    case TRPL_EUNSUPPORTED: return "unsupported shape (need 2 <= L <= 2048, curves <= 8, observation files <= 4)";
     case TRPL_ECUDA: return "CUDA runtime error";
     case TRPL_ENODEVICE: return "no usable CUDA device";
     default: return "unknown error";

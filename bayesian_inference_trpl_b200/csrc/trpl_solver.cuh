@@ -275,7 +275,8 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     const double mag = (a.mag_col >= 0) ? a.x[s * a.ldx + a.mag_col] : 0.0;
 
     // ---- geometry of this lane
-    const int last_lane = (L - 1) / M;         // lane owning node L-1 (at j = M-1 since L % M == 0)
+    const int last_lane = (L - 1) / M;         // lane owning node L-1 ...
+    const int jl = PAD ? (L - 1) % M : M - 1;  // ... at local index jl (M-1 on exact-fit grids)
     bool ev[M + 1];                            // edge m = M*g + j is an interior edge (1..L-1)
 #pragma unroll
     for (int j = 0; j <= M; j++) {
@@ -287,7 +288,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     bool nv[M];                                // node n = M*g + j exists
 #pragma unroll
     for (int j = 0; j < M; j++) nv[j] = PAD ? (M * g + j < L) : true;
-    // surface rows: lane 0 applies the front surface to j=0, last_lane the back surface to j=M-1
+    // surface rows: lane 0 applies the front surface to j=0, last_lane the back surface to j=jl
     const bool is_first = (g == 0), is_last = (g == last_lane);
     const double srf = is_first ? sr0 : (is_last ? srL : 0.0);
 
@@ -515,15 +516,28 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 }
                 // surface recombination rows                                 (pvSimPCR.py:164-170)
                 {
-                    const double Ns = is_first ? N[0] : N[M - 1];
-                    const double Ps = is_first ? P[0] : P[M - 1];
+                    double Nb = N[M - 1], Pb = P[M - 1];        // back-surface node of this lane
+                    if (PAD) {
+#pragma unroll
+                        for (int j = 0; j < M - 1; j++) { Nb = (j == jl) ? N[j] : Nb; Pb = (j == jl) ? P[j] : Pb; }
+                    }
+                    const double Ns = is_first ? N[0] : Nb;
+                    const double Ps = is_first ? P[0] : Pb;
                     const double rs = rcp64(Ns + Ps);
                     const double nd = (srf * fma(Ps, Ps, N0P0)) * (rs * rs);        // = -ds0
                     const double db = fma(-nd, Ns, (srf * fma(Ns, Ps, -N0P0)) * rs);
                     d[0] += is_first ? nd : 0.0;
                     b[0] -= is_first ? db : 0.0;
-                    d[M - 1] += is_last ? nd : 0.0;
-                    b[M - 1] -= is_last ? db : 0.0;
+                    if (PAD) {
+#pragma unroll
+                        for (int j = 0; j < M; j++) {
+                            d[j] += (is_last && j == jl) ? nd : 0.0;
+                            b[j] -= (is_last && j == jl) ? db : 0.0;
+                        }
+                    } else {
+                        d[M - 1] += is_last ? nd : 0.0;
+                        b[M - 1] -= is_last ? db : 0.0;
+                    }
                 }
                 if (PAD) {
 #pragma unroll
@@ -574,15 +588,28 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     b[j] = fma(nds, Pj, -fma(g, npp, bP[j]));
                 }
                 {
-                    const double Ns = is_first ? N[0] : N[M - 1];
-                    const double Ps = is_first ? P[0] : P[M - 1];
+                    double Nb = N[M - 1], Pb = P[M - 1];        // back-surface node of this lane
+                    if (PAD) {
+#pragma unroll
+                        for (int j = 0; j < M - 1; j++) { Nb = (j == jl) ? N[j] : Nb; Pb = (j == jl) ? P[j] : Pb; }
+                    }
+                    const double Ns = is_first ? N[0] : Nb;
+                    const double Ps = is_first ? P[0] : Pb;
                     const double rs = rcp64(Ns + Ps);
                     const double nd = (srf * fma(Ns, Ns, N0P0)) * (rs * rs);
                     const double db = fma(-nd, Ps, (srf * fma(Ns, Ps, -N0P0)) * rs);
                     d[0] += is_first ? nd : 0.0;
                     b[0] -= is_first ? db : 0.0;
-                    d[M - 1] += is_last ? nd : 0.0;
-                    b[M - 1] -= is_last ? db : 0.0;
+                    if (PAD) {
+#pragma unroll
+                        for (int j = 0; j < M; j++) {
+                            d[j] += (is_last && j == jl) ? nd : 0.0;
+                            b[j] -= (is_last && j == jl) ? db : 0.0;
+                        }
+                    } else {
+                        d[M - 1] += is_last ? nd : 0.0;
+                        b[M - 1] -= is_last ? db : 0.0;
+                    }
                 }
                 if (PAD) {
 #pragma unroll

@@ -68,7 +68,8 @@ def test_pvsim_dropin_matches_reference_golden(trpl, name):
 # forward model vs oracle at real grid sizes
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("L,length", [(128, 2000.0), (128, 311.0), (64, 1000.0), (32, 500.0),
-                                      (256, 2000.0), (96, 1500.0), (16, 250.0), (8, 125.0)])
+                                      (256, 2000.0), (96, 1500.0), (16, 250.0), (8, 125.0),
+                                      (70, 1100.0), (33, 500.0), (131, 2000.0), (3, 47.0), (2, 31.0)])
 def test_solve_pl_matches_oracle(trpl, oracle, L, length):
     T = 1500 if L <= 128 else 400
     Time = 0.025 * T
@@ -382,7 +383,8 @@ def test_likelihood_properties_at_full_size(trpl):
 # ------------------------------------------------------------------------------------------------
 # fine grids: one CTA of W warps per simulation (BASELINE config 5 shape: L = 1000)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("L,T", [(1000, 250), (512, 300), (1024, 120), (2048, 60), (260, 300)])
+@pytest.mark.parametrize("L,T", [(1000, 250), (512, 300), (1024, 120), (2048, 60), (260, 300),
+                                 (257, 200), (1001, 120), (774, 150)])
 def test_fine_grid_cta_kernel_matches_oracle(trpl, oracle, L, T):
     length = 2000.0
     simPar = [length, 0.025 * T, L, T, 1, (0,), 7, 10000]
@@ -565,7 +567,7 @@ def test_raw_cabi_binding_as_documented_in_integration_md(trpl, oracle):
     # argument errors come back as codes, not exceptions or crashes
     assert lib.trpl_solve_pl(d_mat.data_ptr(), 5, 11, d_ini.data_ptr(), length, Time, L, T, 1, 7, 10000, 5, 0,
                              d_pl.data_ptr(), 0, T + 1, None, None, 0, None) == -1
-    assert lib.trpl_solve_pl(d_mat.data_ptr(), 5, 12, d_ini.data_ptr(), length, Time, 70, T, 1, 7, 10000, 5, 0,
+    assert lib.trpl_solve_pl(d_mat.data_ptr(), 5, 12, d_ini.data_ptr(), length, Time, 4096, T, 1, 7, 10000, 5, 0,
                              d_pl.data_ptr(), 0, T + 1, None, None, 0, None) == -2
     assert lib.trpl_solve_pl(d_mat.data_ptr(), 5, 12, d_ini.data_ptr(), length, Time, L, T, 1, 7, 10000, 5, 0,
                              d_pl.data_ptr(), 0, T + 1, None, None, 99, None) == -4
