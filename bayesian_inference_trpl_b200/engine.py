@@ -96,20 +96,27 @@ class Problem:
         if len(self.lengths) != self.C:
             raise ValueError("one thickness per excitation curve is required")
         self.E = len(e_data)
-        if self.C > MAX_CURVES or self.E > MAX_EXP:
-            raise TrplError("at most %d curves and %d observation files per fused call"
-                            % (MAX_CURVES, MAX_EXP))
         if init_mode != "points":
             raise ValueError("Problem takes point-wise excitation profiles")
         self.init = [to_device_f64(iniPar[c], self.dev) for c in range(self.C)]
         self.obs = [[ObservationSet(exp[0][c], exp[1][c], self.Time, self.T, self.dev)
                      for c in range(self.C)] for exp in e_data]
-        self.curves = (_lib.Curve * self.C)()
-        for c in range(self.C):
-            self.curves[c].d_init = self.init[c].data_ptr()
-            self.curves[c].length = self.lengths[c]
-            for e in range(self.E):
-                self.obs[e][c].fill(self.curves[c].obs[e])
+        # One fused launch covers up to MAX_CURVES curves x MAX_EXP observation files; larger
+        # problems are tiled (curve tiles accumulate into the same lnL rows, file tiles fill
+        # different rows -- at the price of re-running the forward model for every file tile).
+        self.parts = []
+        for e0 in range(0, self.E, MAX_EXP):
+            e1 = min(self.E, e0 + MAX_EXP)
+            for c0 in range(0, self.C, MAX_CURVES):
+                c1 = min(self.C, c0 + MAX_CURVES)
+                curves = (_lib.Curve * (c1 - c0))()
+                for c in range(c0, c1):
+                    curves[c - c0].d_init = self.init[c].data_ptr()
+                    curves[c - c0].length = self.lengths[c]
+                    for e in range(e0, e1):
+                        self.obs[e][c].fill(curves[c - c0].obs[e - e0])
+                self.parts.append((e0, e1, c0, c1, curves))
+        self.curves = self.parts[0][4]
 
     def steps_per_sample(self):
         """Time steps actually integrated per sample (sum over curves, causal truncation included)."""
@@ -151,17 +158,22 @@ def solve_loglik(X, problem, log_pl=True, self_normalize=False, emulate_f32=Fals
     if lnl is None:
         lnl = torch.zeros((E, S), dtype=torch.float64, device=dev)
     assert lnl.shape == (E, S) and lnl.is_contiguous()
-    sse = torch.empty((E, C, S), dtype=torch.float64, device=dev)
     status = torch.zeros(S, dtype=torch.int32, device=dev)
     iters = torch.zeros((C, S), dtype=torch.int64, device=dev) if want_iters else None
     flags = ((F_LOG_PL if log_pl else 0) | (F_SELF_NORMALIZE if self_normalize else 0)
              | (F_EMULATE_F32 if emulate_f32 else 0))
     mag_col = 12 if X.shape[1] > 12 else -1
-    rc = _lib.lib().trpl_solve_loglik(
-        _ptr(X), S, _row_stride(X), mag_col, problem.curves, C, E, problem.Time, problem.L, problem.T,
-        problem.tol, problem.MAX, int(max_order), flags, _ptr(sse), _ptr(lnl), _ptr(status),
-        _ptr(iters), dev.index, _stream(dev))
-    check(rc, "trpl_solve_loglik")
+    for e0, e1, c0, c1, curves in problem.parts:
+        sse = torch.empty((e1 - e0, c1 - c0, S), dtype=torch.float64, device=dev)
+        st = status if len(problem.parts) == 1 else torch.zeros(S, dtype=torch.int32, device=dev)
+        rc = _lib.lib().trpl_solve_loglik(
+            _ptr(X), S, _row_stride(X), mag_col, curves, c1 - c0, e1 - e0, problem.Time, problem.L,
+            problem.T, problem.tol, problem.MAX, int(max_order), flags, _ptr(sse), _ptr(lnl[e0:e1]),
+            _ptr(st), _ptr(iters[c0:c1]) if (iters is not None and e0 == 0) else None, dev.index,
+            _stream(dev))
+        check(rc, "trpl_solve_loglik")
+        if st is not status:
+            status |= st
     return lnl, status, iters
 
 

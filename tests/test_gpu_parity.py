@@ -678,3 +678,26 @@ def test_fused_path_marks_nonconverged_samples(trpl, oracle):
     np.testing.assert_array_equal(np.isnan(got), np.isnan(ref[0]))
     ok = st == 0
     np.testing.assert_allclose(got[ok], ref[0][ok], rtol=1e-6)
+
+
+def test_more_curves_and_files_than_one_launch_holds(trpl, oracle):
+    """10 curves x 5 observation files: tiled over launches of <= 8 curves x <= 4 files."""
+    L, T = 64, 60
+    rng = np.random.default_rng(8)
+    lengths = [float(v) for v in rng.uniform(300, 2000, 10)]
+    simPar = [lengths, 0.025 * T, L, T, 1, (0,), 7, 10000]
+    inis = np.stack([a * 1e-21 * np.exp(-6e-3 * (np.arange(L) + 0.5) * (lengths[c] / L))
+                     for c, a in enumerate(10 ** rng.uniform(16, 18, 10))])
+    grid = np.linspace(0, simPar[1], T + 1)
+    e_data = []
+    for e in range(5):
+        idx = [np.sort(rng.choice(T + 1, size=rng.integers(5, T), replace=False)) for _ in range(10)]
+        e_data.append(([grid[i] for i in idx], [rng.uniform(-8, -5, len(i)) for i in idx],
+                       [np.full(len(i), 0.1) for i in idx]))
+    X = prior_samples(6, seed=55, mag=True)
+    ref = oracle.loglik(X, simPar, inis, e_data, solver="pcr")
+    prob = trpl.engine.Problem(simPar, inis, e_data, device=0)
+    assert len(prob.parts) == 4
+    lnl, status, iters = trpl.engine.solve_loglik(torch.from_numpy(X).cuda(), prob, want_iters=True)
+    assert (status.cpu().numpy() == 0).all() and iters.shape == (10, 6) and (iters.cpu().numpy() > 0).all()
+    np.testing.assert_allclose(lnl.cpu().numpy(), ref, rtol=1e-6, atol=1e-9)
