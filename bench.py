@@ -288,6 +288,8 @@ def main():
             "gpu_launches": (2 + (3 if world > 1 else 0)) * args.steps,   # sim + finish (+ 3 lse kernels when sharded)
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": traffic,
+                         "note": "neither HBM- nor tensor-bound: scalar FP64 with no dense contraction "
+                                 "(north_star); HBM side given in hbm_* keys, see DESIGN.md section 4",
                          "kernel": "trpl_sim_kernel<4,false>", "kernel_ms": kern_mean,
                          "flops_per_launch": flops_per_step,
                          "peak_source": "DFMA microbenchmark (trpl_bench_dfma) measured in this run; "
