@@ -12,6 +12,8 @@ Cases
   pvsim_stiff_f64    high surface recombination / short lifetime corner, L=16
   probs              probs.prob and probs.fastlog                            (probs.py:49-85)
   bayes              bayeslib.bayes end to end, 2 curves, 1 observation file (bayeslib.py:207)
+  bayes_norm2        same with self_normalize=True and two observation files
+  bayes_lin          same with log_pl=False (linear PL residuals)
   legacy             Legacy/pvSim.py (numba njit CPU solver, BDF2, no Auger) at L=128
 """
 import os
@@ -107,7 +109,7 @@ def case_probs():
                 log_in64=x64_in, log_out64=x64, log_in32=x32_pos_in, log_out32=x32_pos, MIN=MIN)
 
 
-def case_bayes():
+def case_bayes(self_normalize=False, log_pl=True, n_exp=1, num_points=5):
     """bayeslib.bayes, unmodified, on the simulator (3-line get_current_device shim)."""
     from numba import cuda
 
@@ -125,16 +127,25 @@ def case_bayes():
     iniPar = np.stack([excitation(L, 1.2e16, length=length[0]), excitation(L, 1.1e17, length=length[1])])
     rng = np.random.default_rng(3)
     # observations: every 2nd grid time, arbitrary smooth log curve
-    t_obs = [np.linspace(0, Time, T + 1)[::2].copy() for _ in range(2)]
-    v_obs = [rng.uniform(-8, -6, len(t)) for t in t_obs]
-    u_obs = [np.full(len(t), 0.1) for t in t_obs]
-    e_data = [(t_obs, v_obs, u_obs)]
+    e_data = []
+    for e in range(n_exp):
+        t_obs = [np.linspace(0, Time, T + 1)[::2 + e].copy() for _ in range(2)]
+        if self_normalize:      # curves normalised to their own maximum, like bayes_io.get_data does
+            v_obs = [np.sort(rng.uniform(0.05, 1.0, len(t)))[::-1].copy() for t in t_obs]
+            for v in v_obs:
+                v[0] = 1.0
+            if log_pl:
+                v_obs = [np.log10(v) for v in v_obs]
+        else:
+            v_obs = [rng.uniform(-8, -6, len(t)) if log_pl else 10 ** rng.uniform(-8, -6, len(t)) for t in t_obs]
+        u_obs = [np.full(len(t), 0.1) for t in t_obs]
+        e_data.append((t_obs, v_obs, u_obs))
     minX = np.array([1e8, 1e14, 1, 1, 1e-11, 0.1, 0.1, 1e-30, 1e-30, 1, 1, 0.1, -0.5]) * UC
     maxX = np.array([1e8, 1e16, 50, 50, 1e-9, 100, 100, 1e-28, 1e-28, 1000, 2000, 0.1, 0.5]) * UC
     do_log = np.array([1, 1, 0, 0, 1, 1, 1, 1, 1, 0, 0, 1, 0])
     sim_flags = {"load_PL_from_file": False, "override_equal_auger": False,
-                 "override_equal_mu": False, "override_equal_s": True, "log_pl": True,
-                 "self_normalize": False, "random_sample": True, "num_points": 5}
+                 "override_equal_mu": False, "override_equal_s": True, "log_pl": log_pl,
+                 "self_normalize": self_normalize, "random_sample": True, "num_points": num_points}
     gpu_info = {"sims_per_gpu": 2, "num_gpus": 1, "has_GPU": True,
                 "threads_per_block": (L,), "max_sims_per_block": 1}
     np.random.seed(42)
@@ -142,9 +153,13 @@ def case_bayes():
     N, P, X = bayeslib.bayes(pvSimPCR.pvSim, np.array([0]), None, minX, maxX, do_log, iniPar,
                              list(simPar), e_data, sim_flags, gpu_info)
     print("  bayes took %.1fs" % (time.time() - t0), flush=True)
-    return dict(P=P, X=X, minX=minX, maxX=maxX, do_log=do_log, iniPar=iniPar,
-                length=np.array(length), Time=Time, L=L, T=T,
-                t_obs=np.array(t_obs), v_obs=np.array(v_obs), u_obs=np.array(u_obs))
+    out = dict(P=P, X=X, minX=minX, maxX=maxX, do_log=do_log, iniPar=iniPar,
+               length=np.array(length), Time=Time, L=L, T=T, n_exp=n_exp,
+               self_normalize=self_normalize, log_pl=log_pl)
+    for e, (t_obs, v_obs, u_obs) in enumerate(e_data):
+        sfx = "" if e == 0 else "_%d" % e
+        out["t_obs" + sfx] = np.array(t_obs); out["v_obs" + sfx] = np.array(v_obs); out["u_obs" + sfx] = np.array(u_obs)
+    return out
 
 
 def case_legacy():
@@ -176,6 +191,8 @@ CASES = {
     "pvsim_stiff_f64": lambda: run_pvsim(16, 20, 3, np.float64, "points", 4, stiff=True, amp=1.6485e18),
     "probs": case_probs,
     "bayes": case_bayes,
+    "bayes_norm2": lambda: case_bayes(self_normalize=True, log_pl=True, n_exp=2, num_points=3),
+    "bayes_lin": lambda: case_bayes(self_normalize=False, log_pl=False, n_exp=1, num_points=3),
     "legacy": case_legacy,
 }
 

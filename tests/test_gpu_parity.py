@@ -701,3 +701,30 @@ def test_more_curves_and_files_than_one_launch_holds(trpl, oracle):
     lnl, status, iters = trpl.engine.solve_loglik(torch.from_numpy(X).cuda(), prob, want_iters=True)
     assert (status.cpu().numpy() == 0).all() and iters.shape == (10, 6) and (iters.cpu().numpy() > 0).all()
     np.testing.assert_allclose(lnl.cpu().numpy(), ref, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["bayes_norm2", "bayes_lin"])
+def test_bayes_mirror_flags_match_reference_golden(trpl, name):
+    """self_normalize / two observation files / log_pl=False: this package's bayes() (fused, float32
+    emulation) vs the unmodified reference bayeslib.bayes recorded on the simulator."""
+    path = os.path.join(GOLDEN, "cudasim_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    g = golden("cudasim_%s.npz" % name)
+    L, T = int(g["L"]), int(g["T"])
+    simPar = [list(g["length"]), float(g["Time"]), L, T, 1, (0,), 7, 10000]
+    e_data = []
+    for e in range(int(g["n_exp"])):
+        sfx = "" if e == 0 else "_%d" % e
+        e_data.append((list(g["t_obs" + sfx]), list(g["v_obs" + sfx]), list(g["u_obs" + sfx])))
+    sim_flags = {"load_PL_from_file": False, "override_equal_auger": False, "override_equal_mu": False,
+                 "override_equal_s": True, "log_pl": bool(g["log_pl"]), "self_normalize": bool(g["self_normalize"]),
+                 "random_sample": True, "num_points": len(g["X"])}
+    for fused in (True, False):
+        gpu_info = {"sims_per_gpu": 2, "num_gpus": 1, "fused": fused, "emulate_f32": True}
+        trpl.bayes_validate.connect_to_gpu(gpu_info, nthreads=128, sims_per_block=1)
+        np.random.seed(42)
+        N, P, X = trpl.bayeslib.bayes(trpl.pvSim, np.array([0]), None, g["minX"], g["maxX"], g["do_log"],
+                                      g["iniPar"], list(simPar), e_data, sim_flags, gpu_info)
+        np.testing.assert_array_equal(X, g["X"])
+        np.testing.assert_allclose(P, g["P"], rtol=3e-5)

@@ -132,3 +132,27 @@ def test_oracle_pipeline_matches_reference_bayes():
     e_data = [(list(g["t_obs"]), list(g["v_obs"]), list(g["u_obs"]))]
     P = oracle.loglik(g["X"], simPar, g["iniPar"], e_data, emulate_f32=True, solver="pcr")
     np.testing.assert_allclose(P, g["P"], rtol=2e-6)
+
+
+def _edata_from_golden(g):
+    e_data = []
+    for e in range(int(g["n_exp"]) if "n_exp" in g.files else 1):
+        sfx = "" if e == 0 else "_%d" % e
+        e_data.append((list(g["t_obs" + sfx]), list(g["v_obs" + sfx]), list(g["u_obs" + sfx])))
+    return e_data
+
+
+@pytest.mark.parametrize("name", ["bayes_norm2", "bayes_lin"])
+def test_oracle_pipeline_flags_match_reference_bayes(name):
+    """self_normalize=True with two observation files, and log_pl=False, through the unmodified
+    reference bayeslib.bayes on the simulator vs oracle.loglik(emulate_f32=True)."""
+    path = os.path.join(GOLDEN, "cudasim_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    g = golden("cudasim_%s.npz" % name)
+    L, T = int(g["L"]), int(g["T"])
+    simPar = [list(g["length"]), float(g["Time"]), L, T, 1, (0,), 7, 10000]
+    P = oracle.loglik(g["X"], simPar, g["iniPar"], _edata_from_golden(g), log_pl=bool(g["log_pl"]),
+                      self_normalize=bool(g["self_normalize"]), emulate_f32=True, solver="pcr")
+    assert P.shape == g["P"].shape
+    np.testing.assert_allclose(P, g["P"], rtol=5e-6)
