@@ -67,6 +67,17 @@ void make_scales(double length, double time, int L, int T, double *sc, double *d
     *dx_o = dx; *dt_o = dt;
 }
 
+// stream-ordered device scratch, released on every exit path
+struct Scratch {
+    void *p = nullptr;
+    cudaStream_t st;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+    ~Scratch() { if (p) cudaFreeAsync(p, st); }
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+};
+
 struct Cfg { int M; bool pad; int W; };      // W = warps per simulation (1: warp kernel, >1: CTA kernel)
 int pick_cfg(int L, Cfg *cfg)
 {
@@ -169,10 +180,10 @@ int launch_sims(KArgs &ka, const Cfg &cfg, int device, cudaStream_t st)
         for (int j = i; j > 0 && ka.curves[ka.curve_order[j]].t_last > ka.curves[ka.curve_order[j - 1]].t_last; j--) {
             const int t = ka.curve_order[j]; ka.curve_order[j] = ka.curve_order[j - 1]; ka.curve_order[j - 1] = t;
         }
-    unsigned long long *counter = nullptr;
-    CK(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-    ka.counter = counter;
+    Scratch counter(st);
+    CK(counter.alloc(sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+    ka.counter = (unsigned long long *)counter.p;
     int threads, spc; size_t smem2;
     cfg_shape(cfg, &threads, &spc, &smem2);
     const unsigned long long items = (unsigned long long)ka.S * ka.C;
@@ -183,7 +194,6 @@ int launch_sims(KArgs &ka, const Cfg &cfg, int device, cudaStream_t st)
         k<<<grid, threads, smem, st>>>(ka);
         CK(cudaGetLastError());
     }
-    CK(cudaFreeAsync(counter, st));
     return TRPL_OK;
 }
 
@@ -288,9 +298,6 @@ int trpl_solve_loglik(const double *d_x, int64_t S, int64_t ldx, int mag_col,
     ka.sse = d_sse; ka.iters = (long long *)d_iters;
     ka.mag_col = mag_col; ka.C = C; ka.E = E; ka.L = L; ka.plT = 1; ka.max_iter = max_iter;
     ka.max_order = max_order; ka.flags = flags; ka.pl_dtype = TRPL_F64;
-    int *status_cs = nullptr;
-    if (d_status) CK(cudaMallocAsync((void **)&status_cs, sizeof(int) * (size_t)C * S, st));
-    ka.status = status_cs;
     for (int c = 0; c < C; c++) {
         const trpl_curve &src = curves[c];
         if (!src.d_init || !(src.length > 0)) return TRPL_EINVAL;
@@ -312,13 +319,15 @@ int trpl_solve_loglik(const double *d_x, int64_t S, int64_t ldx, int mag_col,
             if (o.n > 0 && o.hi_max > cv.t_last) cv.t_last = o.hi_max;   // causal truncation
         }
     }
+    Scratch status_cs(st);                     // allocated only after every argument was validated
+    if (d_status) CK(status_cs.alloc(sizeof(int) * (size_t)C * S));
+    ka.status = (int *)status_cs.p;
     rc = launch_sims(ka, cfg, device, st);
     if (rc) return rc;
     const int tb = 256;
-    trpl_finish_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, st>>>(d_sse, d_lnl, status_cs, d_status,
-                                                                      S, C, E);
+    trpl_finish_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, st>>>(d_sse, d_lnl, (const int *)status_cs.p,
+                                                                      d_status, S, C, E);
     CK(cudaGetLastError());
-    if (status_cs) CK(cudaFreeAsync(status_cs, st));
     return TRPL_OK;
 }
 
