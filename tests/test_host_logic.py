@@ -205,3 +205,25 @@ def test_bayes_io_matches_reference_reader():
             for c in range(len(e[0])):
                 np.testing.assert_array_equal(np.asarray(e[k][c]), g["%s_%s%d" % (name, part, c)])
         np.testing.assert_array_equal(bayes_io.get_initpoints(exc, ic), g[name + "_ini"])
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """On a machine without CUDA every product entry point raises instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for GPU-less machines")
+    import bayesian_inference_trpl_b200 as trpl
+    pl = np.zeros((1, 5))
+    with pytest.raises(trpl.TrplError):
+        trpl.pvSim(pl, None, None, None, np.ones((1, 12)), [100.0, 1.0, 8, 4, 1, (0,), 7, 100], np.ones(8),
+                   (8,), 1, 1, init_mode="points")
+    with pytest.raises(trpl.TrplError):
+        trpl.fastlog(np.ones((2, 2)), 1e-300)
+    with pytest.raises(trpl.TrplError):
+        trpl.prob(np.zeros(2), np.ones((2, 3)), np.ones(3), np.ones(3), np.zeros(2))
+    with pytest.raises((trpl.TrplError, RuntimeError)):
+        trpl.bayeslib.simulate(trpl.pvSim, [], np.zeros((1, 1)), np.ones((1, 13)), [None], [None], 1,
+                               [100.0, 1.0, 8, 4, 1, (0,), 7, 100], np.ones((1, 8)),
+                               {"load_PL_from_file": False, "log_pl": True, "self_normalize": False},
+                               {"has_GPU": False, "sims_per_gpu": 1, "num_gpus": 1}, 0,
+                               np.zeros(1), np.zeros(1), np.zeros(1))
