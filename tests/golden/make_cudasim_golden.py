@@ -12,6 +12,7 @@ Cases
   pvsim_stiff_f64    high surface recombination / short lifetime corner, L=16
   pvsim_L32_f64      L=32 (four PCR stages + 2x2 finish)
   pvsim_L128_f64     the production grid L=128 (six PCR stages), BDF ramp 1..5, 7 steps
+  pvsim_long_f64     L=8, 241 steps at the highest excitation: BDF5 steady state with Auger on
   probs              probs.prob and probs.fastlog                            (probs.py:49-85)
   bayes              bayeslib.bayes end to end, 2 curves, 1 observation file (bayeslib.py:207)
   bayes_norm2        same with self_normalize=True and two observation files
@@ -193,6 +194,7 @@ CASES = {
     "pvsim_stiff_f64": lambda: run_pvsim(16, 20, 3, np.float64, "points", 4, stiff=True, amp=1.6485e18),
     "pvsim_L32_f64": lambda: run_pvsim(32, 10, 2, np.float64, "points", 5, amp=1.1539e17),
     "pvsim_L128_f64": lambda: run_pvsim(128, 6, 1, np.float64, "points", 6, amp=1.6485e18),
+    "pvsim_long_f64": lambda: run_pvsim(8, 240, 2, np.float64, "points", 7, amp=1.6485e18),
     "probs": case_probs,
     "bayes": case_bayes,
     "bayes_norm2": lambda: case_bayes(self_normalize=True, log_pl=True, n_exp=2, num_points=3),

@@ -63,3 +63,33 @@ def pl_noise_floor(matpar_phys, length, time, L, T):
 def simpar_from_golden(g):
     length, Time, L, T, plT, tol, MAX = g["simPar"]
     return [float(length), float(Time), int(L), int(T), int(plT), (0,), int(tol), int(MAX)]
+
+
+def route_a_case(inis, S=256, T=4000, truth_pl=None):
+    """Inputs of the `bayeslib.bayes` comparison between the reference's own kernels and the drop-ins
+    (tools/ref_on_b200.py, tests/test_reference_b200.py): default prior with a free mag_offset, 3
+    power-scan curves at L=128, observation windows shorter than the simulation, the last one
+    off the step grid.  `truth_pl(c)` -> PL of the truth sample for curve c on the full step grid."""
+    L = 128
+    Time = 0.025 * T
+    simPar = [2000.0, Time, L, T, 1, (0,), 7, 10000]
+    lo, hi = MINX * UC, MAXX * UC
+    lo[2:4] = 0.5 * UC[2]
+    lo[12], hi[12] = -0.2, 0.2
+    grid = np.linspace(0, Time, T + 1)
+    e_t, e_v, e_u = [], [], []
+    for c in range(3):
+        n = [1501, 2201, 3001][c]
+        tt = np.linspace(0, grid[n - 1], n)
+        if c == 2:
+            tt = tt[:-1] + 0.3 * 0.025          # off-grid
+        e_t.append(tt)
+        e_u.append(np.full(len(tt), 0.1))
+        if truth_pl is not None:
+            e_v.append(np.interp(tt, grid, np.log10(truth_pl(c))))
+    flags = {"load_PL_from_file": False, "log_pl": True, "self_normalize": False, "random_sample": True,
+             "num_points": S, "override_equal_mu": False, "override_equal_s": False,
+             "override_equal_auger": False}
+    info = {"has_GPU": True, "sims_per_gpu": 128, "num_gpus": 1, "threads_per_block": (128,),
+            "max_sims_per_block": 1}
+    return dict(simPar=simPar, lo=lo, hi=hi, do_log=DO_LOG, e_data=[(e_t, e_v, e_u)], flags=flags, info=info)
