@@ -105,17 +105,30 @@ def simulate(model, e_data, P, X, plI, plI_int, num_curves, sim_params, init_par
     if gpu_info.get("fused", True):
         sp = list(sim_params)
         sp[0] = thick
-        problem = engine.Problem(sp, init_params, e_data, device=dev.index)
-        rows = np.concatenate([np.arange(b, b + n) for b, n in blocks])
-        Xd = engine.to_device_f64(X[rows], dev)
+        problem = engine.cached_problem(sp, init_params, e_data, device=dev.index)
+        if len(blocks) == 1 or num_gpus == 1:
+            lo, hi = blocks[0][0], blocks[-1][0] + blocks[-1][1]
+            rows = slice(lo, hi)
+            Xrows = X[lo:hi]
+        else:
+            rows = np.concatenate([np.arange(b, b + n) for b, n in blocks])
+            Xrows = X[rows]
+        # host -> pinned staging -> device, result device -> pinned -> P: one copy each way per call
+        xh = engine.pinned("X", Xrows.shape, torch.float64)
+        xh.numpy()[...] = Xrows
+        Xd = xh.to(dev, non_blocking=True)
         torch.cuda.synchronize(dev)
         clock0 = time.perf_counter()
         lnl, status, _ = engine.solve_loglik(Xd, problem, log_pl=log_pl, self_normalize=normalize,
                                              emulate_f32=gpu_info.get("emulate_f32", False))
-        lnl_h = lnl.cpu().numpy()
+        lh = engine.pinned("lnl", lnl.shape, torch.float64)
+        sh = engine.pinned("status", status.shape, torch.int32)
+        lh.copy_(lnl, non_blocking=True)
+        sh.copy_(status, non_blocking=True)
+        torch.cuda.synchronize(dev)
         solver_time[gpu_id] += time.perf_counter() - clock0
-        P[:, rows] += lnl_h
-        bad = int((status != 0).sum().item())
+        P[:, rows] += lh.numpy()
+        bad = int(np.count_nonzero(sh.numpy()))
         if bad and logger is not None:
             logger.warning("%d samples did not converge (lnL = NaN for them)", bad)
         return
@@ -150,18 +163,54 @@ def simulate(model, e_data, P, X, plI, plI_int, num_curves, sim_params, init_par
 
 def rank_and_world():
     """(gpu_id, num_ranks) of this process: SLURM array task (the reference's launcher,
-    bayeslib.py:231), else torchrun's RANK/WORLD_SIZE, else a single rank."""
+    bayeslib.py:231; the task count comes from SLURM_ARRAY_TASK_COUNT when SLURM exports it), else
+    torchrun's RANK/WORLD_SIZE, else a single rank.  num_ranks is None when unknown."""
     if os.getenv("SLURM_ARRAY_TASK_ID") is not None:
-        return int(os.getenv("SLURM_ARRAY_TASK_ID")), None
+        cnt = os.getenv("SLURM_ARRAY_TASK_COUNT")
+        return int(os.getenv("SLURM_ARRAY_TASK_ID")), (int(cnt) if cnt is not None else None)
     if os.getenv("RANK") is not None:
         return int(os.getenv("RANK")), int(os.getenv("WORLD_SIZE", "1"))
     return 0, None
 
 
+def _bayes_philox(N, num_exp, minX, maxX, do_log, init_params, sim_params, e_data, sim_flags, gpu_info, logger):
+    """sim_flags["sampler"] == "philox": every rank draws ONLY its own contiguous rows of the sample
+    matrix on its GPU (counter-based Philox4x32-10, `first_sample` = first row of the shard, so the
+    shards of any world size concatenate to the single-rank draw bit for bit), runs the fused path on
+    them and the tables are all-gathered once at the end.  X never crosses PCIe on the way in; the
+    bounds arrive already in engine units (parallel_bayes_gpu.py:183-184), so the unit conversion is
+    part of the draw."""
+    import torch.distributed as dist
+    from . import distributed
+    dev = engine.require_cuda(gpu_info.get("device", None))
+    S = int(sim_flags["num_points"])
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    lo, hi = distributed.shard_bounds(S, rank, world)
+    flags = ((1 if sim_flags["override_equal_mu"] else 0) | (2 if sim_flags["override_equal_s"] else 0)
+             | (4 if sim_flags["override_equal_auger"] else 0))
+    Xd = engine.random_grid_device(minX, maxX, do_log, hi - lo, int(sim_flags.get("seed", 42)),
+                                   first_sample=lo, override_flags=flags, device=dev.index)
+    problem = engine.cached_problem(list(sim_params), init_params, e_data, device=dev.index)
+    lnl, status, _ = engine.solve_loglik(Xd, problem, log_pl=sim_flags["log_pl"],
+                                         self_normalize=sim_flags["self_normalize"],
+                                         emulate_f32=gpu_info.get("emulate_f32", False))
+    bad = int((status != 0).sum().item())
+    if bad and logger is not None:
+        logger.warning("%d samples did not converge (lnL = NaN for them)", bad)
+    P = distributed.gather_rows(lnl, S)
+    X = distributed.gather_rows(Xd.t().contiguous(), S).t()
+    return np.arange(S), P.cpu().numpy(), np.ascontiguousarray(X.cpu().numpy())
+
+
 def bayes(model, N, P, minX, maxX, do_log, init_params, sim_params, e_data, sim_flags, gpu_info,
           logger=None):
     """Draw the sample matrix, evaluate this rank's share of the likelihood table, return
-    (N, P, X) like bayeslib.bayes (bayeslib.py:207-252)."""
+    (N, P, X) like bayeslib.bayes (bayeslib.py:207-252).  Columns of P that belong to other ranks
+    stay 0 exactly as in the reference (bayes_io.py:134) -- except with sim_flags["sampler"] ==
+    "philox", where the complete table comes back on every rank."""
+    if sim_flags.get("sampler", "numpy") == "philox":
+        return _bayes_philox(N, len(e_data), minX, maxX, do_log, init_params, sim_params, e_data,
+                             sim_flags, gpu_info, logger)
     num_gpus = gpu_info["num_gpus"]
     solver_time = np.zeros(num_gpus)
     err_sq_time = np.zeros(num_gpus)
@@ -180,3 +229,11 @@ def bayes(model, N, P, minX, maxX, do_log, init_params, sim_params, e_data, sim_
         logger.info("Total err_sq time: %s, avg %s", err_sq_time, np.mean(err_sq_time))
         logger.info("Total misc time: %s, avg %s", misc_time, np.mean(misc_time))
     return N, P, X
+
+
+def owned_columns(n, gpu_info, gpu_id):
+    """Boolean mask of the columns of P this rank computed (block-cyclic layout, bayeslib.py:131)."""
+    m = np.zeros(n, dtype=bool)
+    for b, size in _my_blocks(n, gpu_info["sims_per_gpu"], gpu_id, gpu_info["num_gpus"]):
+        m[b:b + size] = True
+    return m

@@ -123,7 +123,7 @@ __global__ void trpl_lse_sum_kernel(const double *x, long long n, double *out)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
         const double v = x[i];
-        if (v == v) acc += exp(v - mx);
+        if (v == v && v > -INFINITY) acc += exp(v - mx);   // -inf entries weigh 0 (also when every entry is -inf)
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -316,7 +316,7 @@ trpl_moments_kernel_fixed(const double *x, long long ldx, const double *w, long 
             const double wx = ww * r[j];
             sx[j] += wx;
 #pragma unroll
-            for (int k = j; k < NC; k++) sxx[q++] = fma(wx, r[k], sxx[q]);
+            for (int k = j; k < NC; k++) { sxx[q] = fma(wx, r[k], sxx[q]); q++; }
         }
     }
     const bool lead = (threadIdx.x & 31) == 0;

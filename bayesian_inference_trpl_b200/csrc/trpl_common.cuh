@@ -17,6 +17,16 @@ constexpr int WARPS_PER_CTA = 4;
 #ifndef TRPL_MIN_CTAS
 #define TRPL_MIN_CTAS 4
 #endif
+// A/B switches of the solver (defaults = the shipped configuration; profiles/r02_variants.txt)
+#ifndef TRPL_MINOR_PIVOTS
+#define TRPL_MINOR_PIVOTS 0        // 1: pivot reciprocals from leading minors (independent, 3 more DMUL)
+#endif
+#ifndef TRPL_CONST_TABLE
+#define TRPL_CONST_TABLE 1         // 1: derived per-simulation constants parked in lanes and read by shuffles
+#endif
+#ifndef TRPL_PCR_LAST_EXP
+#define TRPL_PCR_LAST_EXP 35       // off-diagonals below 2^-this: the PCR stage degenerates to a B-only update
+#endif
 
 struct ObsDev {
     int n;

@@ -79,7 +79,7 @@ struct Scratch {
 };
 
 struct Cfg { int M; bool pad; int W; };      // W = warps per simulation (1: warp kernel, >1: CTA kernel)
-int pick_cfg(int L, Cfg *cfg)
+int pick_cfg(int L, int flags, Cfg *cfg)
 {
     if (L < 2) return TRPL_EINVAL;
     if (L <= 256) {
@@ -90,9 +90,9 @@ int pick_cfg(int L, Cfg *cfg)
         return TRPL_OK;
     }
     // fine grids: one CTA of W warps per simulation; 8 nodes per lane (fewer interface unknowns,
-    // less PCR work per node than 4; TRPL_FINE_M4=1 selects 4 for A/B tests)
+    // less PCR work per node than 4; the TRPL_F_FINE_M4 flag bit selects 4 for A/B tests)
     if (L > 256 * 8) return TRPL_EUNSUPPORTED;
-    const int M = (getenv("TRPL_FINE_M4") == nullptr) ? 8 : 4;
+    const int M = (flags & TRPL_F_FINE_M4) ? 4 : 8;
     int W = 2;
     while (32 * M * W < L) W <<= 1;
     if (W > 16) return TRPL_EUNSUPPORTED;
@@ -158,16 +158,27 @@ int kernel_geometry(int device, const Cfg &cfg, kern_t *k_out, size_t *smem_out,
     return TRPL_OK;
 }
 
-int check_device(int device)
-{
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
-        cudaGetLastError();
-        return TRPL_ENODEVICE;
+// Makes `device` current for the duration of one C-ABI call and restores the caller's device on every
+// exit path (torch reads its current device from the runtime; a library must not change it).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    int enter(int device)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+            cudaGetLastError();
+            return TRPL_ENODEVICE;
+        }
+        CK(cudaGetDevice(&prev));
+        if (prev != device) {
+            CK(cudaSetDevice(device));
+            switched = true;
+        }
+        return TRPL_OK;
     }
-    CK(cudaSetDevice(device));
-    return TRPL_OK;
-}
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 int launch_sims(KArgs &ka, const Cfg &cfg, int device, cudaStream_t st)
 {
@@ -223,9 +234,10 @@ const char *trpl_last_cuda_error(void) { return g_cuda_err; }
 int trpl_resident_sims(int device, int L)
 {
     Cfg cfg;
-    int rc = pick_cfg(L, &cfg);
+    int rc = pick_cfg(L, 0, &cfg);
     if (rc) return rc;
-    rc = check_device(device);
+    DeviceGuard guard;
+    rc = guard.enter(device);
     if (rc) return rc;
     kern_t k; size_t smem; int nb, nsm;
     rc = kernel_geometry(device, cfg, &k, &smem, &nb, &nsm);
@@ -245,9 +257,10 @@ int trpl_solve_pl(const double *d_matpar, int64_t S, int64_t ld_matpar, const do
         (pl_dtype != TRPL_F64 && pl_dtype != TRPL_F32))
         return TRPL_EINVAL;
     Cfg cfg;
-    int rc = pick_cfg(L, &cfg);
+    int rc = pick_cfg(L, flags, &cfg);
     if (rc) return rc;
-    rc = check_device(device);
+    DeviceGuard guard;
+    rc = guard.enter(device);
     if (rc) return rc;
     if (S == 0) return TRPL_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -283,9 +296,10 @@ int trpl_solve_loglik(const double *d_x, int64_t S, int64_t ldx, int mag_col,
         return TRPL_EINVAL;
     if (C > TRPL_MAX_CURVES || E > TRPL_MAX_EXP) return TRPL_EUNSUPPORTED;
     Cfg cfg;
-    int rc = pick_cfg(L, &cfg);
+    int rc = pick_cfg(L, flags, &cfg);
     if (rc) return rc;
-    rc = check_device(device);
+    DeviceGuard guard;
+    rc = guard.enter(device);
     if (rc) return rc;
     if (S == 0) return TRPL_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -334,7 +348,8 @@ int trpl_solve_loglik(const double *d_x, int64_t S, int64_t ldx, int mag_col,
 int trpl_log10_clamp(void *d_pl, int dtype, int64_t n, double min, int device, void *stream)
 {
     if (!d_pl || n < 0 || (dtype != TRPL_F64 && dtype != TRPL_F32)) return TRPL_EINVAL;
-    int rc = check_device(device);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc) return rc;
     if (n == 0) return TRPL_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -355,7 +370,8 @@ int trpl_lnp_accumulate(double *d_P, const double *d_pl, int64_t S, int64_t n, i
                         const double *d_values, const double *d_mag, int device, void *stream)
 {
     if (!d_P || !d_pl || !d_values || !d_mag || S < 0 || n < 0 || ld < n) return TRPL_EINVAL;
-    int rc = check_device(device);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc) return rc;
     if (S == 0) return TRPL_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -402,7 +418,8 @@ int trpl_obs_prepare(const double *times, int32_t n, double time, int T, int32_t
 int trpl_lse_partial(const double *d_x, int64_t n, double *d_out2, int device, void *stream)
 {
     if (!d_x || !d_out2 || n < 0) return TRPL_EINVAL;
-    int rc = check_device(device);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     trpl_lse_init_kernel<<<1, 1, 0, st>>>(d_out2);
@@ -425,7 +442,8 @@ int trpl_random_grid(double *d_x, int64_t S, int64_t ldx, const double *minx, co
                      uint64_t first_sample, int device, void *stream)
 {
     if (!d_x || !minx || !maxx || !do_log || S < 0 || ncol < 1 || ncol > 16 || ldx < ncol) return TRPL_EINVAL;
-    int rc = check_device(device);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc) return rc;
     if (S == 0) return TRPL_OK;
     GridArgs ga;
@@ -451,7 +469,8 @@ int trpl_random_grid(double *d_x, int64_t S, int64_t ldx, const double *minx, co
 int trpl_posterior_weights(const double *d_lnp, int64_t n, double lse, double *d_w, int device, void *stream)
 {
     if (!d_lnp || !d_w || n < 0) return TRPL_EINVAL;
-    int rc = check_device(device);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc) return rc;
     if (n == 0) return TRPL_OK;
     int nsm = 0;
@@ -473,7 +492,8 @@ int trpl_weighted_hist(const double *d_x, int64_t n, int64_t ldx, int colx, int 
     if (coly >= 0 && (nby < 1 || !(hiy > loy))) return TRPL_EINVAL;
     const long long nb = (long long)nbx * (coly >= 0 ? nby : 1);
     if (nb > 8192) return TRPL_EUNSUPPORTED;
-    int rc = check_device(device);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc) return rc;
     if (n == 0) return TRPL_OK;
     int nsm = 0;
@@ -493,7 +513,8 @@ int trpl_weighted_moments(const double *d_x, int64_t n, int64_t ldx, int ncol, c
                           double *d_out, int device, void *stream)
 {
     if (!d_x || !d_w || !d_out || n < 0 || ncol < 1 || ncol > 15 || ldx < ncol) return TRPL_EINVAL;
-    int rc = check_device(device);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc) return rc;
     if (n == 0) return TRPL_OK;
     int nsm = 0;
@@ -519,7 +540,8 @@ int trpl_weighted_moments(const double *d_x, int64_t n, int64_t ldx, int ncol, c
 int trpl_bench_dfma(int device, int iters, double *tflops, double *ms)
 {
     if (!tflops || iters < 1) return TRPL_EINVAL;
-    int rc = check_device(device);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc) return rc;
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));

@@ -109,6 +109,22 @@ struct Comm {
     }
 };
 
+// one normalised PCR stage: row i absorbs rows i-rf (vm) and i+rf (vp); {L,U,B} with unit diagonal
+__device__ __forceinline__ void pcr_stage(double &Lr, double &Ur, double &Br, const double (&vm)[3],
+                                          const double (&vp)[3])
+{
+    const double Lm = vm[0], Um = vm[1], Bm = vm[2];
+    const double Lp = vp[0], Up = vp[1], Bp = vp[2];
+    const double D = fma(-Lp, Ur, fma(-Um, Lr, 1.0));
+    const double B = fma(-Bp, Ur, fma(-Bm, Lr, Br));
+    const double Ln = -Lm * Lr;
+    const double Un = -Up * Ur;
+    const double inv = rcp64(D);
+    Br = B * inv;
+    Lr = Ln * inv;
+    Ur = Un * inv;
+}
+
 // Tridiagonal solve, M rows per lane (row n = M*g + j):  l[j] x[n-1] + d[j] x[n] + u[j] x[n+1] = b[j].
 // Rows outside the physical system must be identity rows (l=u=0, d=1).  l of the first row
 // and u of the last physical row must be 0.
@@ -118,13 +134,14 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
                                                 const double (&u)[M], const double (&b)[M],
                                                 double (&x)[M], Comm<W> &cm)
 {
+    // [sec:partition]
     double Lr, Dr, Ur, Br;
     double c[M > 1 ? M - 1 : 1], y[M > 1 ? M - 1 : 1], v[M > 1 ? M - 1 : 1], w[M > 1 ? M - 1 : 1];
     if constexpr (M > 1) {
         // interior rows 0..M-2:  x_j = y_j - v_j * s_left - w_j * s_own
+#if TRPL_MINOR_PIVOTS
         // Pivot reciprocals from the leading principal minors m_{j+1} = d_j m_j - l_j u_{j-1} m_{j-1}
-        // (1/pivot_j = m_j / m_{j+1}): the M-1 reciprocals are independent of each other, so
-        // their MUFU+Newton chains overlap instead of forming one serial chain.
+        // (1/pivot_j = m_j / m_{j+1}): independent reciprocals, 3 more multiplies per solve.
         double ip[M - 1];
         {
             double mm[M];                 // mm[j] = m_{j+1}
@@ -145,6 +162,22 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
             y[j] = fma(-l[j], y[j - 1], b[j]) * ip[j];
             v[j] = (-l[j] * v[j - 1]) * ip[j];
         }
+#else
+        // Thomas forward sweep: pivot_j = d_j - l_j c_{j-1}
+        {
+            const double ip0 = rcp64(d[0]);
+            c[0] = u[0] * ip0;
+            y[0] = b[0] * ip0;
+            v[0] = l[0] * ip0;
+        }
+#pragma unroll
+        for (int j = 1; j < M - 1; j++) {
+            const double ipj = rcp64(fma(-l[j], c[j - 1], d[j]));
+            c[j] = u[j] * ipj;
+            y[j] = fma(-l[j], y[j - 1], b[j]) * ipj;
+            v[j] = (-l[j] * v[j - 1]) * ipj;
+        }
+#endif
         w[M - 2] = c[M - 2];
 #pragma unroll
         for (int j = M - 3; j >= 0; j--) {
@@ -164,37 +197,44 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
     } else {
         Lr = l[0]; Dr = d[0]; Ur = u[0]; Br = b[0];
     }
-    // parallel cyclic reduction over the 32*W interface unknowns, unit diagonal
+    // [sec:normalise] parallel cyclic reduction over the 32*W interface unknowns, unit diagonal
     {
         double inv = rcp64(Dr);
         Lr *= inv; Ur *= inv; Br *= inv;
     }
+    // [sec:pcr]
 #pragma unroll
     for (int rf = 1; rf < 32 * W; rf <<= 1) {
-        // Off-diagonals shrink quadratically per stage; once every |L|,|U| of the simulation is
-        // below 2^-70 the remaining stages cannot change D = 1 or B in the last bit: stop.
+        // Off-diagonals shrink quadratically per stage.  Let m = max |L|,|U| over the simulation:
+        //   m < 2^-70: the remaining stages cannot change D = 1 or B in the last bit: stop;
+        //   m < 2^-35: this is the last stage, and in it D = 1 - O(m^2) rounds to exactly 1 and the new
+        //              off-diagonals are < 2^-70, so only B needs updating (bit-identical to a full
+        //              stage followed by the stop above): one third of the exchange, 2 FMAs.
         // (Not tested before the first three stages: a coupling that small after two stages means
-        // an initial one below 2^-17, i.e. practically no transport; those cases just run 3 stages.)
+        // an initial one below 2^-9, i.e. practically no transport; those cases just run 3 stages.)
         const int hl = __double2hiint(Lr) & 0x7fffffff, hu = __double2hiint(Ur) & 0x7fffffff;
-        const bool busy = (rf < 8) || (max(hl, hu) >= ((1023 - 70) << 20));
-        double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
+        const int hm = max(hl, hu);
+        const bool busy = (rf < 8) || (hm >= ((1023 - TRPL_PCR_LAST_EXP) << 20));
         if constexpr (W == 1) {
-            if (rf >= 8 && !__any_sync(FULL, busy)) break;
+            if (rf >= 8 && !__any_sync(FULL, busy)) {
+                if (__any_sync(FULL, hm >= ((1023 - 70) << 20))) {
+                    double mine[1] = {Br}, vm[1], vp[1];
+                    cm.template xchg<1, true, true>(mine, rf, rf, vm, vp);
+                    Br = fma(-vp[0], Ur, fma(-vm[0], Lr, Br));
+                }
+                break;
+            }
+            double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
             cm.template xchg<3, true, true>(mine, rf, rf, vm, vp);
+            pcr_stage(Lr, Ur, Br, vm, vp);
         } else {
-            if (!cm.template xchg<3, true, true>(mine, rf, rf, vm, vp, busy)) break;
+            double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
+            const bool busy70 = (rf < 8) || (hm >= ((1023 - 70) << 20));
+            if (!cm.template xchg<3, true, true>(mine, rf, rf, vm, vp, busy70)) break;
+            pcr_stage(Lr, Ur, Br, vm, vp);
         }
-        const double Lm = vm[0], Um = vm[1], Bm = vm[2];
-        const double Lp = vp[0], Up = vp[1], Bp = vp[2];
-        const double D = fma(-Lp, Ur, fma(-Um, Lr, 1.0));
-        const double B = fma(-Bp, Ur, fma(-Bm, Lr, Br));
-        const double Ln = -Lm * Lr;
-        const double Un = -Up * Ur;
-        const double inv = rcp64(D);
-        Br = B * inv;
-        Lr = Ln * inv;
-        Ur = Un * inv;
     }
+    // [sec:backsubst]
     x[M - 1] = Br;
     const double sl = cm.from_prev(Br);
     if constexpr (M > 1) {
@@ -204,6 +244,7 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
     return sl;
 }
 
+// [sec:none]
 // lane-private ring of the 4 older BDF levels: [slot 0..3][field N,P,E][M doubles per lane]
 template <int M>
 struct Ring {
@@ -258,6 +299,46 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     const bool emu32 = (flags & TRPL_F_EMULATE_F32) != 0;
 
     // ---- parameters: non-dimensionalise (pvSimPCR.py:327-331), one column per lane, then broadcast
+#if TRPL_CONST_TABLE
+    // Every per-simulation constant, raw or derived, is computed once, parked in one lane of `ctab`
+    // and read back with a constant-lane shuffle: ptxas proves such a value warp-uniform and can
+    // hold it in a uniform register; a derived constant it could recompute (tauP*N0P0 ...) would be
+    // rematerialised inside the Newton loop as a product of two uniform values, which forces one of
+    // them into a vector register for all of its uses (3-register DFMAs, +50 % issue time each).
+    double ctab;
+    {
+        double raw = 0.0;
+        if (lane < TRPL_NPAR) raw = a.x[s * a.ldx + lane] * cv.scales[lane];
+        const double rN0 = __shfl_sync(FULL, raw, 0), rP0 = __shfl_sync(FULL, raw, 1);
+        const double rDN = __shfl_sync(FULL, raw, 2), rDP = __shfl_sync(FULL, raw, 3);
+        const double rtN = __shfl_sync(FULL, raw, 9), rtP = __shfl_sync(FULL, raw, 10);
+        const double rLam = __shfl_sync(FULL, raw, 11);
+        const double n0p0 = rN0 * rP0;
+        ctab = raw;                                   // lanes 0..11: the scaled parameters
+        ctab = (lane == 12) ? n0p0 : ctab;
+        ctab = (lane == 13) ? 0.5 * rDN : ctab;
+        ctab = (lane == 14) ? 0.5 * rDP : ctab;
+        ctab = (lane == 15) ? rtP * n0p0 : ctab;
+        ctab = (lane == 16) ? rtN * n0p0 : ctab;
+        ctab = (lane == 17) ? rLam * rDP : ctab;
+        ctab = (lane == 18) ? rLam * rDN : ctab;
+        ctab = (lane == 19) ? 0.5 * (rLam * rDP) : ctab;
+        ctab = (lane == 20) ? 0.5 * (rLam * rDN) : ctab;
+        ctab = (lane == 21) ? -(double)L * n0p0 : ctab;
+    }
+    const double DN = __shfl_sync(FULL, ctab, 2), DP = __shfl_sync(FULL, ctab, 3);
+    const double rate = __shfl_sync(FULL, ctab, 4);
+    const double sr0 = __shfl_sync(FULL, ctab, 5), srL = __shfl_sync(FULL, ctab, 6);
+    const double CN = __shfl_sync(FULL, ctab, 7), CP = __shfl_sync(FULL, ctab, 8);
+    const double tauN = __shfl_sync(FULL, ctab, 9), tauP = __shfl_sync(FULL, ctab, 10);
+    const double N0 = __shfl_sync(FULL, ctab, 0), P0 = __shfl_sync(FULL, ctab, 1);
+    const double N0P0 = __shfl_sync(FULL, ctab, 12);
+    const double hDN = __shfl_sync(FULL, ctab, 13), hDP = __shfl_sync(FULL, ctab, 14);
+    const double tauP_N0P0 = __shfl_sync(FULL, ctab, 15), tauN_N0P0 = __shfl_sync(FULL, ctab, 16);
+    const double LamDP = __shfl_sync(FULL, ctab, 17), LamDN = __shfl_sync(FULL, ctab, 18);
+    const double hLamDP = __shfl_sync(FULL, ctab, 19), hLamDN = __shfl_sync(FULL, ctab, 20);
+    const double mLN0P0 = __shfl_sync(FULL, ctab, 21);   // pvSimPCR.py:278
+#else
     double mpl = 0.0;
     if (lane < TRPL_NPAR) mpl = a.x[s * a.ldx + lane] * cv.scales[lane];
     const double N0 = __shfl_sync(FULL, mpl, 0), P0 = __shfl_sync(FULL, mpl, 1);
@@ -269,8 +350,9 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     const double Lam = __shfl_sync(FULL, mpl, 11);
     const double N0P0 = N0 * P0;
     const double hDN = 0.5 * DN, hDP = 0.5 * DP;
-    const double CN_N0P0 = CN * N0P0, CP_N0P0 = CP * N0P0;
     const double LamDP = Lam * DP, LamDN = Lam * DN, hLamDP = 0.5 * LamDP, hLamDN = 0.5 * LamDN;
+    const double mLN0P0 = -(double)L * N0P0;   // pvSimPCR.py:278
+#endif
     const double TOL = a.TOL;
     const double mag = (a.mag_col >= 0) ? a.x[s * a.ldx + a.mag_col] : 0.0;
 
@@ -332,7 +414,6 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     }
     double En = 0.0;   // E on edge M*g + M (owned by the next lane)
 
-    const double mLN0P0 = -(double)L * N0P0;   // pvSimPCR.py:278
     const int t_last = cv.t_last;
     const int plT = a.plT;
     const int n_pl = t_last / plT + 1;
@@ -392,8 +473,13 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 if (slo < 0) y_lo = lp_carry;
                 double sq = 0.0;
                 if (mine) {
-                    // scipy interp1d._call_linear: w_hi*y_hi + w_lo*y_lo, no contraction
-                    const double yi = __dadd_rn(__dmul_rn(ob.whi[i], y_hi), __dmul_rn(ob.wlo[i], y_lo));
+                    // scipy interp1d._call_linear: w_hi*y_hi + w_lo*y_lo, no contraction.  An
+                    // observation exactly on a grid point has a zero weight on the other neighbour: take
+                    // the value itself (the reference's on-grid bypass reads plI directly,
+                    // bayeslib.py:173-183), so that 0 * -inf (PL <= 0 under the f32 clamp) is not NaN.
+                    const double wh = ob.whi[i], wl = ob.wlo[i];
+                    const double yi = (wl == 0.0) ? y_hi : (wh == 0.0) ? y_lo
+                                                  : __dadd_rn(__dmul_rn(wh, y_hi), __dmul_rn(wl, y_lo));
                     double err = yi + mag;                  // probs.py:33-38
                     err -= ob.val[i];
                     sq = err * err;
@@ -448,6 +534,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             else if (order == 4) { a0 = 25.0 / 12; a1 = -4.0; a2 = 3.0; a3 = -4.0 / 3; a4 = 0.25; }
             else { a0 = 137.0 / 60; a1 = -5.0; a2 = 5.0; a3 = -10.0 / 3; a4 = 1.25; a5 = -0.2; }
         }
+        const double a0p2DN = fma(2.0, DN, a0), a0p2DP = fma(2.0, DP, a0);   // diagonal with both neighbours
 
         // ---- history sums bU = a1 U(t) + a2 U(t-1) + ... + a5 U(t-4)       (pvSimPCR.py:133-135)
         double bN[M], bP[M], bE[M];
@@ -479,7 +566,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             ring.store(slot, 2, E);
         }
 
-        // ---- Newton / Gauss-Seidel iteration                              (pvSimPCR.py:147-216)
+        // [sec:loop] ---- Newton / Gauss-Seidel iteration                   (pvSimPCR.py:147-216)
         int it = 0;
         bool nonfinite = false;
         for (;;) {
@@ -487,34 +574,39 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             double zN = 0.0, zP = 0.0;    // sum(|residual| - TOL*|b|): err < TOL  <=>  z < 0
             bool converged_now = false, nonfinite_now = false;
 
-            // ======== N system (P, E frozen) ========
+            // Assembly notes (both species).  With e = E/2 on an edge the reference's rows are
+            //   l_j = D(+-e_j - 1),  u_j = D(-+e_{j+1} - 1),  d_j = a0 - u_{j-1} - l_{j+1} - ds
+            // (pvSimPCR.py:148-161,178-190), so d_j = a0 + 2D +- D(e_j - e_{j+1}) - ds: one FMA on the
+            // edge difference dE (shared by the two species).  A missing neighbour (front of node 0,
+            // back of node L-1: E = 0 there) takes one D off the diagonal and zeroes the off-diagonal;
+            // that correction rides on the surface-recombination rows, which touch the same two nodes.
+            // SRH: (P*tp - tauP*np)/tp^2 = (tauN*P^2 + tauP*N0P0)/tp^2 exactly, one product fewer and
+            // no cancellation.  -ds = P*(B + CP*P + 2*CN*N) + srh - CN*N0P0 (Auger terms regrouped so
+            // that CN*N, CP*P + CN*N and B + ... are shared with the rhs factor).
+
+            // [sec:N-assembly] ======== N system (P, E frozen) ========
             {
-                double cu[M + 1], cl[M + 1];   // edge coefficients: cu[m] = upper of row m-1, cl[m] = lower of row m
-#pragma unroll
-                for (int j = 0; j <= M; j++) {
-                    const double Ej = (j < M) ? E[j] : En;
-                    cu[j] = sel(ev[j], fma(-hDN, Ej, -DN), 0.0);     // DN*(-E/2 - 1)
-                    cl[j] = sel(ev[j], fma(hDN, Ej, -DN), 0.0);      // DN*(+E/2 - 1)
-                }
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     const double Nj = N[j], Pj = P[j];
-                    const double tp = fma(Nj, tauP, Pj * tauN);
-                    const double NP = Nj * Pj;
-                    const double npp = NP - N0P0;
+                    const double pt = Pj * tauN;
+                    const double tp = fma(Nj, tauP, pt);
+                    const double npp = fma(Nj, Pj, -N0P0);
                     const double r = rcp64(tp);
-                    const double q = fma(-tauP, npp, Pj * tp);
-                    const double srh = (q * r) * r;
-                    const double cnN = CN * Nj;
-                    const double aug = fma(Pj, fma(CP, Pj, cnN + cnN), -CN_N0P0);   // CN*N*P + CP*P^2 + CN*np
-                    const double nds = fma(rate, Pj, srh) + aug;             // = -ds
-                    l[j] = cl[j];
-                    u[j] = cu[j + 1];
-                    d[j] = ((a0 - cu[j]) - cl[j + 1]) + nds;
-                    const double g = fma(CP, Pj, cnN) + (rate + r);
-                    b[j] = fma(nds, Nj, -fma(g, npp, bN[j]));
+#if TRPL_CONST_TABLE
+                    const double qr = fma(pt, Pj, tauP_N0P0) * r;
+#else
+                    const double qr = fma(-tauP, npp, Pj * tp) * r;
+#endif
+                    const double hr = fma(CP, Pj, CN * Nj) + rate;
+                    const double nds = fma(Pj, hr, fma(CN, npp, qr * r));               // = -ds
+                    const double Ep = (j < M - 1) ? E[j + 1] : En;
+                    l[j] = fma(hDN, E[j], -DN);                                          // DN*(+E/2 - 1)
+                    u[j] = fma(-hDN, Ep, -DN);                                           // DN*(-E/2 - 1)
+                    d[j] = fma(hDN, E[j] - Ep, nds + a0p2DN);
+                    b[j] = fma(nds, Nj, -fma(hr + r, npp, bN[j]));
                 }
-                // surface recombination rows                                 (pvSimPCR.py:164-170)
+                // [sec:N-surface] surface recombination rows (pvSimPCR.py:164-170) + missing-neighbour fix
                 {
                     double Nb = N[M - 1], Pb = P[M - 1];        // back-surface node of this lane
                     if (PAD) {
@@ -524,31 +616,37 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double Ns = is_first ? N[0] : Nb;
                     const double Ps = is_first ? P[0] : Pb;
                     const double rs = rcp64(Ns + Ps);
-                    const double nd = (srf * fma(Ps, Ps, N0P0)) * (rs * rs);        // = -ds0
-                    const double db = fma(-nd, Ns, (srf * fma(Ns, Ps, -N0P0)) * rs);
-                    d[0] += is_first ? nd : 0.0;
-                    b[0] -= is_first ? db : 0.0;
+                    const double srs = srf * rs;
+                    const double nd = fma(Ps, Ps, N0P0) * (srs * rs);                   // = -ds0
+                    const double db = fma(-nd, Ns, fma(Ns, Ps, -N0P0) * srs);
+                    const double ndm = nd - DN;
                     if (PAD) {
 #pragma unroll
                         for (int j = 0; j < M; j++) {
-                            d[j] += (is_last && j == jl) ? nd : 0.0;
-                            b[j] -= (is_last && j == jl) ? db : 0.0;
+                            const bool at = (is_first && j == 0) || (is_last && j == jl);
+                            d[j] += at ? ndm : 0.0;
+                            b[j] -= at ? db : 0.0;
                         }
                     } else {
-                        d[M - 1] += is_last ? nd : 0.0;
+                        d[0] += is_first ? ndm : 0.0;
+                        b[0] -= is_first ? db : 0.0;
+                        d[M - 1] += is_last ? ndm : 0.0;
                         b[M - 1] -= is_last ? db : 0.0;
                     }
                 }
                 if (PAD) {
 #pragma unroll
                     for (int j = 0; j < M; j++) {
-                        l[j] = sel(nv[j], l[j], 0.0);
-                        u[j] = sel(nv[j], u[j], 0.0);
+                        l[j] = sel(nv[j] && ev[j], l[j], 0.0);
+                        u[j] = sel(nv[j] && ev[j + 1], u[j], 0.0);
                         d[j] = sel(nv[j], d[j], 1.0);
                         b[j] = sel(nv[j], b[j], 0.0);
                     }
+                } else {
+                    l[0] = sel(is_first, 0.0, l[0]);
+                    u[M - 1] = sel(is_last, 0.0, u[M - 1]);
                 }
-                // L1 residual of the current iterate                         (pvSimPCR.py:172, :14-40)
+                // [sec:N-residual] L1 residual of the current iterate         (pvSimPCR.py:172, :14-40)
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     const double xm = (j == 0) ? Nl : N[j - 1];
@@ -556,39 +654,37 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double res = fma(l[j], xm, fma(d[j], N[j], fma(u[j], xp, -b[j])));
                     zN = fma(-TOL, fabs(b[j]), zN + fabs(res));
                 }
+                // [sec:N-solve]
                 Nl = tridiag_solve<M, W>(l, d, u, b, N, cm);
+                // [sec:N-exchange]
                 Nr = cm.from_next(N[0]);
             }
 
-            // ======== P system (new N) ========
+            // [sec:P-assembly] ======== P system (new N) ========
             {
-                double cu[M + 1], cl[M + 1];
-#pragma unroll
-                for (int j = 0; j <= M; j++) {
-                    const double Ej = (j < M) ? E[j] : En;
-                    cu[j] = sel(ev[j], fma(hDP, Ej, -DP), 0.0);      // DP*(+E/2 - 1)
-                    cl[j] = sel(ev[j], fma(-hDP, Ej, -DP), 0.0);     // DP*(-E/2 - 1)
-                }
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     const double Nj = N[j], Pj = P[j];
-                    const double tp = fma(Nj, tauP, Pj * tauN);
-                    const double NP = Nj * Pj;
-                    const double npp = NP - N0P0;
+                    const double nt = Nj * tauP;
+                    const double tp = fma(Pj, tauN, nt);
+                    const double npp = fma(Nj, Pj, -N0P0);
                     const double r = rcp64(tp);
-                    const double q = fma(-tauN, npp, Nj * tp);
-                    const double srh = (q * r) * r;
-                    const double cpP = CP * Pj;
-                    const double aug = fma(Nj, fma(CN, Nj, cpP + cpP), -CP_N0P0);   // CP*N*P + CN*N^2 + CP*np
-                    const double nds = fma(rate, Nj, srh) + aug;
-                    l[j] = cl[j];
-                    u[j] = cu[j + 1];
-                    d[j] = ((a0 - cu[j]) - cl[j + 1]) + nds;
-                    const double g = fma(CN, Nj, cpP) + (rate + r);
-                    b[j] = fma(nds, Pj, -fma(g, npp, bP[j]));
+#if TRPL_CONST_TABLE
+                    const double qr = fma(nt, Nj, tauN_N0P0) * r;
+#else
+                    const double qr = fma(-tauN, npp, Nj * tp) * r;
+#endif
+                    const double hr = fma(CN, Nj, CP * Pj) + rate;
+                    const double nds = fma(Nj, hr, fma(CP, npp, qr * r));
+                    const double Ep = (j < M - 1) ? E[j + 1] : En;
+                    l[j] = fma(-hDP, E[j], -DP);                                         // DP*(-E/2 - 1)
+                    u[j] = fma(hDP, Ep, -DP);                                            // DP*(+E/2 - 1)
+                    d[j] = fma(-hDP, E[j] - Ep, nds + a0p2DP);
+                    b[j] = fma(nds, Pj, -fma(hr + r, npp, bP[j]));
                 }
+                // [sec:P-surface]
                 {
-                    double Nb = N[M - 1], Pb = P[M - 1];        // back-surface node of this lane
+                    double Nb = N[M - 1], Pb = P[M - 1];
                     if (PAD) {
 #pragma unroll
                         for (int j = 0; j < M - 1; j++) { Nb = (j == jl) ? N[j] : Nb; Pb = (j == jl) ? P[j] : Pb; }
@@ -596,30 +692,37 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double Ns = is_first ? N[0] : Nb;
                     const double Ps = is_first ? P[0] : Pb;
                     const double rs = rcp64(Ns + Ps);
-                    const double nd = (srf * fma(Ns, Ns, N0P0)) * (rs * rs);
-                    const double db = fma(-nd, Ps, (srf * fma(Ns, Ps, -N0P0)) * rs);
-                    d[0] += is_first ? nd : 0.0;
-                    b[0] -= is_first ? db : 0.0;
+                    const double srs = srf * rs;
+                    const double nd = fma(Ns, Ns, N0P0) * (srs * rs);
+                    const double db = fma(-nd, Ps, fma(Ns, Ps, -N0P0) * srs);
+                    const double ndm = nd - DP;
                     if (PAD) {
 #pragma unroll
                         for (int j = 0; j < M; j++) {
-                            d[j] += (is_last && j == jl) ? nd : 0.0;
-                            b[j] -= (is_last && j == jl) ? db : 0.0;
+                            const bool at = (is_first && j == 0) || (is_last && j == jl);
+                            d[j] += at ? ndm : 0.0;
+                            b[j] -= at ? db : 0.0;
                         }
                     } else {
-                        d[M - 1] += is_last ? nd : 0.0;
+                        d[0] += is_first ? ndm : 0.0;
+                        b[0] -= is_first ? db : 0.0;
+                        d[M - 1] += is_last ? ndm : 0.0;
                         b[M - 1] -= is_last ? db : 0.0;
                     }
                 }
                 if (PAD) {
 #pragma unroll
                     for (int j = 0; j < M; j++) {
-                        l[j] = sel(nv[j], l[j], 0.0);
-                        u[j] = sel(nv[j], u[j], 0.0);
+                        l[j] = sel(nv[j] && ev[j], l[j], 0.0);
+                        u[j] = sel(nv[j] && ev[j + 1], u[j], 0.0);
                         d[j] = sel(nv[j], d[j], 1.0);
                         b[j] = sel(nv[j], b[j], 0.0);
                     }
+                } else {
+                    l[0] = sel(is_first, 0.0, l[0]);
+                    u[M - 1] = sel(is_last, 0.0, u[M - 1]);
                 }
+                // [sec:P-residual]
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     const double xm = (j == 0) ? Pl : P[j - 1];
@@ -627,15 +730,17 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double res = fma(l[j], xm, fma(d[j], P[j], fma(u[j], xp, -b[j])));
                     zP = fma(-TOL, fabs(b[j]), zP + fabs(res));
                 }
-                // ---- stop decision for THIS iteration (pvSimPCR.py:213-216): both L1 residuals are
-                // known here, before the P solve; reducing them now lets the shuffle chain overlap
-                // the solve.
+                // [sec:stop-rule] ---- stop decision for THIS iteration (pvSimPCR.py:213-216): both L1
+                // residuals are known here, before the P solve; reducing them now lets the shuffle
+                // chain overlap the solve.
                 cm.stop_rule(zN, zP, converged_now, nonfinite_now);
+                // [sec:P-solve]
                 Pl = tridiag_solve<M, W>(l, d, u, b, P, cm);
+                // [sec:P-exchange]
                 Pr = cm.from_next(P[0]);
             }
 
-            // ======== E update on interior edges                           (pvSimPCR.py:205-209)
+            // [sec:E-update] ======== E update on interior edges             (pvSimPCR.py:205-209)
 #pragma unroll
             for (int j = 0; j < M; j++) {
                 const double Nm = (j == 0) ? Nl : N[j - 1];
@@ -644,14 +749,15 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 const double num = fma(LamDP, P[j] - Pm, fma(-LamDN, N[j] - Nm, -bE[j]));
                 E[j] = sel(ev[j], num * rcp64(den), 0.0);
             }
-            En = cm.from_next(E[0]);
+            En = sel(ev[M], cm.from_next(E[0]), 0.0);      // no edge beyond the back surface
 
-            // ======== stop rule (pvSimPCR.py:213-216): decided by the flags computed before the P solve
+            // [sec:loop] ======== stop rule (pvSimPCR.py:213-216): decided by the flags computed before the P solve
             it++;
             if (nonfinite_now) { nonfinite = true; break; }
             if (converged_now) break;
             if (it >= a.max_iter) break;
         }
+        // [sec:step]
         iters_total += it;
         if (nonfinite || it >= a.max_iter) {                 // pvSimPCR.py:269-274
             status |= nonfinite ? TRPL_ST_NONFINITE : TRPL_ST_NOCONV;
@@ -690,6 +796,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     __syncwarp();
 }
 
+// [sec:kernel]
 template <int M, bool PAD>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, TRPL_MIN_CTAS)
 trpl_sim_kernel(const __grid_constant__ KArgs a)

@@ -86,6 +86,9 @@ class Problem:
     def __init__(self, simPar, iniPar, e_data, device=None, init_mode="points"):
         self.dev = require_cuda(device)
         Length, Time, L, T, plT, pT, tol, MAX = simPar
+        if int(plT) != 1:
+            raise ValueError("the fused likelihood path samples PL on every step (plT = 1, what bayeslib's "
+                             "[S, T+1] buffer requires, bayeslib.py:137); got plT = %r" % (plT,))
         self.Time, self.L, self.T, self.tol, self.MAX = float(Time), int(L), int(T), int(tol), int(MAX)
         iniPar = np.asarray(iniPar, dtype=np.float64)
         self.C = iniPar.shape[0]
@@ -121,6 +124,47 @@ class Problem:
     def steps_per_sample(self):
         """Time steps actually integrated per sample (sum over curves, causal truncation included)."""
         return sum(max(self.obs[e][c].hi_max for e in range(self.E)) + 1 for c in range(self.C))
+
+
+_PROBLEMS = {}          # digest -> Problem, insertion-ordered (small LRU)
+_PINNED = {}            # (tag, shape, dtype) -> pinned host staging tensor
+
+
+def cached_problem(simPar, iniPar, e_data, device=None, keep=4):
+    """Problem for these inputs, staged on the device once and reused while the CONTENT of
+    (simPar, iniPar, e_data) is unchanged (bayeslib.simulate is called once per run in the reference, but a
+    driver that calls it per batch should not re-bracket and re-upload 240 k observations every time)."""
+    import hashlib
+    dev = require_cuda(device)
+    h = hashlib.blake2b(digest_size=16)
+    Length = simPar[0]
+    h.update(repr((dev.index, [float(v) for v in np.atleast_1d(Length)], float(simPar[1]), int(simPar[2]),
+                   int(simPar[3]), int(simPar[4]), int(simPar[6]), int(simPar[7]), len(e_data))).encode())
+    h.update(np.ascontiguousarray(iniPar, dtype=np.float64).tobytes())
+    for exp in e_data:
+        for c in range(len(exp[0])):
+            h.update(np.ascontiguousarray(exp[0][c], dtype=np.float64).tobytes())
+            h.update(np.ascontiguousarray(exp[1][c], dtype=np.float64).tobytes())
+    key = h.digest()
+    prob = _PROBLEMS.pop(key, None)
+    if prob is None:
+        prob = Problem(simPar, iniPar, e_data, device=dev.index)
+    _PROBLEMS[key] = prob
+    while len(_PROBLEMS) > keep:
+        _PROBLEMS.pop(next(iter(_PROBLEMS)))
+    return prob
+
+
+def pinned(tag, shape, dtype):
+    """Reusable pinned host staging buffer."""
+    key = (tag, tuple(shape), dtype)
+    t = _PINNED.get(key)
+    if t is None:
+        if len(_PINNED) > 16:
+            _PINNED.clear()
+        t = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        _PINNED[key] = t
+    return t
 
 
 def solve_pl(matpar, init, length, time, L, T, plT=1, tol=7, max_iter=10000, out_dtype=torch.float64,

@@ -49,17 +49,25 @@ def default_config():
 
 def run(init_filename, experimental_data_filename, out_filename, cfg=None, seed=42, logger=None,
         posterior=False):
-    """Same sequence as the reference `__main__` block; returns (P, X in common units)."""
+    """Same sequence as the reference `__main__` block; returns (P, X in common units).
+
+    Launchers: (a) torchrun, one rank per GPU: the per-rank tables are merged over NCCL and rank 0
+    exports; (b) SLURM array tasks like the reference (no communication): task k fills its
+    block-cyclic columns and EVERY task exports, into `<out>_task<k>` when there is more than one
+    task, with NaN in the columns it does not own (`merge_task_exports` joins them afterwards);
+    the task count must agree with gpu_info["num_gpus"]."""
     import torch
     import torch.distributed as dist
     cfg = cfg or default_config()
     rank, world = bayeslib.rank_and_world()
-    if world is not None and world > 1 and not dist.is_initialized():
+    slurm = os.getenv("SLURM_ARRAY_TASK_ID") is not None
+    if not slurm and world is not None and world > 1 and not dist.is_initialized():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist.init_process_group("nccl")
     np.random.seed(seed)
     simPar = [cfg["Length"], cfg["Time"], cfg["L"], cfg["T"], cfg["plT"], cfg["pT"], cfg["tol"], cfg["MAX"]]
-    ic_flags, sim_flags, gpu_info = cfg["ic_flags"], cfg["sim_flags"], dict(cfg["gpu_info"])
+    ic_flags, sim_flags, gpu_info = cfg["ic_flags"], dict(cfg["sim_flags"]), dict(cfg["gpu_info"])
+    sim_flags.setdefault("seed", seed)
     minX, maxX, do_log = cfg["minX"].astype(float).copy(), cfg["maxX"].astype(float).copy(), cfg["do_log"]
 
     iniPar = bayes_io.get_initpoints(init_filename, ic_flags)
@@ -74,7 +82,15 @@ def run(init_filename, experimental_data_filename, out_filename, cfg=None, seed=
     bayes_validate.connect_to_gpu(gpu_info, nthreads=128, sims_per_block=1)
     if not gpu_info["has_GPU"]:
         raise RuntimeError("no GPU: the B200 engine has no CPU fallback")
-    if world is not None:
+    if slurm:
+        if world is not None and world != gpu_info["num_gpus"]:
+            raise RuntimeError("SLURM_ARRAY_TASK_COUNT=%d disagrees with gpu_info['num_gpus']=%d: the tasks "
+                               "would leave columns of P uncomputed" % (world, gpu_info["num_gpus"]))
+        if rank >= gpu_info["num_gpus"]:
+            raise RuntimeError("SLURM_ARRAY_TASK_ID=%d but gpu_info['num_gpus']=%d" % (rank, gpu_info["num_gpus"]))
+        if sim_flags.get("sampler", "numpy") == "philox" and gpu_info["num_gpus"] > 1:
+            raise RuntimeError("the philox sampler shards over torch.distributed ranks; use torchrun")
+    elif world is not None:
         gpu_info["num_gpus"] = world
 
     minX *= unit_conversions
@@ -82,20 +98,42 @@ def run(init_filename, experimental_data_filename, out_filename, cfg=None, seed=
     clock0 = perf_counter()
     N, P, X = bayeslib.bayes(pvSim, np.array([0]), None, minX, maxX, do_log, iniPar, simPar, e_data,
                              sim_flags, gpu_info, logger=logger)
-    P = np.asarray(distributed.merge_block_cyclic(P).cpu() if world and world > 1 else P)
+    complete = sim_flags.get("sampler", "numpy") == "philox"
+    if not complete and not slurm and world and world > 1:
+        P = np.asarray(distributed.merge_block_cyclic(P).cpu())
     if logger is not None:
         logger.info("Bayesim took %.3f s", perf_counter() - clock0)
     X = X / unit_conversions
-    if rank == 0:
-        for i, of in enumerate(out_filename):
+    outs = list(out_filename)
+    if slurm and gpu_info["num_gpus"] > 1:
+        mine = bayeslib.owned_columns(P.shape[1], gpu_info, rank)
+        P = np.where(mine[None, :], P, np.nan)             # 0 would read as the best possible likelihood
+        outs = ["%s_task%d" % (of.rstrip("/\\"), rank) for of in outs]
+    if slurm or rank == 0:
+        for i, of in enumerate(outs):
             bayes_io.export(of, P[i], X, logger=logger)
             if posterior:
-                t = torch.from_numpy(P[i]).cuda()
+                t = torch.from_numpy(np.nan_to_num(P[i], nan=-np.inf)).cuda()
                 from . import engine
                 ms = engine.lse_partial(t)
                 lse = ms[0] + torch.log(ms[1])
                 w = distributed.normalize_posterior(t, lse).cpu().numpy()
                 np.save(os.path.join(of, os.path.basename(os.path.normpath(of)) + "_BAYRAN_W.npy"), w)
+    return P, X
+
+
+def merge_task_exports(out_filename, num_tasks):
+    """Join the `<out>_task<k>` exports of a SLURM array run into `<out>`: every column is taken from
+    the task that owns it (the others hold NaN there); a column nobody computed stays NaN."""
+    base = os.path.basename(os.path.normpath(out_filename))
+    P, X = None, None
+    for k in range(num_tasks):
+        d = "%s_task%d" % (out_filename.rstrip("/\\"), k)
+        b = os.path.basename(os.path.normpath(d))
+        Pk = np.load(os.path.join(d, b + "_BAYRAN_P.npy"))
+        X = np.load(os.path.join(d, b + "_BAYRAN_X.npy"))
+        P = Pk.copy() if P is None else np.where(np.isnan(P), Pk, P)
+    bayes_io.export(out_filename, P, X)
     return P, X
 
 
@@ -109,12 +147,19 @@ def main(argv=None):
     ap.add_argument("--time-steps", type=int, default=None)
     ap.add_argument("--final-time", type=float, default=None)
     ap.add_argument("--posterior", action="store_true", help="also write normalised posterior weights")
+    ap.add_argument("--sampler", choices=["numpy", "philox"], default="numpy",
+                    help="numpy: the reference's host draw (np.random.seed(42), bit-compatible); philox: every rank "
+                         "draws only its own rows on its GPU")
+    ap.add_argument("--sims-per-gpu", type=int, default=None)
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)s: %(message)s")
     logger = logging.getLogger("Bayes Logger Main")
     cfg = default_config()
     if args.num_points:
         cfg["sim_flags"]["num_points"] = args.num_points
+    cfg["sim_flags"]["sampler"] = args.sampler
+    if args.sims_per_gpu:
+        cfg["gpu_info"]["sims_per_gpu"] = args.sims_per_gpu
     if args.length:
         cfg["Length"] = args.length[0] if len(args.length) == 1 else list(args.length)
     if args.time_steps:

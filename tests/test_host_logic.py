@@ -227,3 +227,37 @@ def test_no_cpu_fallback_without_a_gpu():
                                {"load_PL_from_file": False, "log_pl": True, "self_normalize": False},
                                {"has_GPU": False, "sims_per_gpu": 1, "num_gpus": 1}, 0,
                                np.zeros(1), np.zeros(1), np.zeros(1))
+
+
+def test_slurm_array_mode_rank_world_and_owned_columns(monkeypatch):
+    """under SLURM arrays the task count must be known or checked, and columns a task does
+    not own must not read as lnL = 0 (the best possible likelihood)."""
+    from bayesian_inference_trpl_b200 import bayeslib
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.setenv("SLURM_ARRAY_TASK_ID", "2")
+    monkeypatch.delenv("SLURM_ARRAY_TASK_COUNT", raising=False)
+    assert bayeslib.rank_and_world() == (2, None)
+    monkeypatch.setenv("SLURM_ARRAY_TASK_COUNT", "4")
+    assert bayeslib.rank_and_world() == (2, 4)
+    info = {"sims_per_gpu": 3, "num_gpus": 4}
+    masks = [bayeslib.owned_columns(29, info, r) for r in range(4)]
+    assert np.array_equal(np.sum(masks, axis=0), np.ones(29, dtype=int))      # a partition of the columns
+    assert masks[2][6:9].all() and not masks[2][:6].any() and masks[2][18:21].all()
+
+
+def test_merge_task_exports(tmp_path):
+    from bayesian_inference_trpl_b200 import bayes_io, bayeslib, parallel_bayes_gpu as entry
+    rng = np.random.default_rng(0)
+    S = 23
+    X = rng.normal(size=(S, 13))
+    P = rng.normal(size=S)
+    info = {"sims_per_gpu": 4, "num_gpus": 3}
+    out = str(tmp_path / "run")
+    for k in range(3):
+        mine = bayeslib.owned_columns(S, info, k)
+        bayes_io.export("%s_task%d" % (out, k), np.where(mine, P, np.nan), X)
+    Pm, Xm = entry.merge_task_exports(out, 3)
+    np.testing.assert_array_equal(Pm, P)
+    np.testing.assert_array_equal(Xm, X)
+    base = os.path.basename(out)
+    np.testing.assert_array_equal(np.load(os.path.join(out, base + "_BAYRAN_P.npy")), P)
