@@ -21,6 +21,9 @@ constexpr int WARPS_PER_CTA = 4;
 #ifndef TRPL_MINOR_PIVOTS
 #define TRPL_MINOR_PIVOTS 0        // 1: pivot reciprocals from leading minors (independent, 3 more DMUL)
 #endif
+#ifndef TRPL_CTA_LAT
+#define TRPL_CTA_LAT 1             // multi-warp simulations: pivots from leading minors (independent reciprocals)
+#endif
 #ifndef TRPL_CONST_TABLE
 #define TRPL_CONST_TABLE 1         // 1: derived per-simulation constants parked in lanes and read by shuffles
 #endif

@@ -79,7 +79,7 @@ struct Scratch {
 };
 
 struct Cfg { int M; bool pad; int W; };      // W = warps per simulation (1: warp kernel, >1: CTA kernel)
-int pick_cfg(int L, int flags, Cfg *cfg)
+int pick_cfg(int L, Cfg *cfg)
 {
     if (L < 2) return TRPL_EINVAL;
     if (L <= 256) {
@@ -89,14 +89,13 @@ int pick_cfg(int L, int flags, Cfg *cfg)
         cfg->M = M; cfg->pad = (L != 32 * M); cfg->W = 1;
         return TRPL_OK;
     }
-    // fine grids: one CTA of W warps per simulation; 8 nodes per lane (fewer interface unknowns,
-    // less PCR work per node than 4; the TRPL_F_FINE_M4 flag bit selects 4 for A/B tests)
+    // fine grids: one CTA of W warps per simulation, 8 nodes per lane (fewer interface unknowns and
+    // less solver work per node than 4: +25 % at L=1000, round 1).  pad = general padding (L % 8 != 0);
+    // otherwise the unused lanes carry a dummy film (run_sim PADM = 1).
     if (L > 256 * 8) return TRPL_EUNSUPPORTED;
-    const int M = (flags & TRPL_F_FINE_M4) ? 4 : 8;
     int W = 2;
-    while (32 * M * W < L) W <<= 1;
-    if (W > 16) return TRPL_EUNSUPPORTED;
-    cfg->M = M; cfg->pad = true; cfg->W = W;
+    while (32 * 8 * W < L) W <<= 1;
+    cfg->M = 8; cfg->pad = (L % 8 != 0); cfg->W = W;
     return TRPL_OK;
 }
 
@@ -104,18 +103,10 @@ typedef void (*kern_t)(const KArgs);
 kern_t pick_kernel(const Cfg &c)
 {
     if (c.W > 1) {
-        if (c.M == 8) {
-            switch (c.W) {
-            case 2: return trpl_sim_cta_kernel<2, 8>;
-            case 4: return trpl_sim_cta_kernel<4, 8>;
-            default: return trpl_sim_cta_kernel<8, 8>;
-            }
-        }
         switch (c.W) {
-        case 2: return trpl_sim_cta_kernel<2, 4>;
-        case 4: return trpl_sim_cta_kernel<4, 4>;
-        case 8: return trpl_sim_cta_kernel<8, 4>;
-        default: return trpl_sim_cta_kernel<16, 4>;
+        case 2: return c.pad ? trpl_sim_cta_kernel<2, 8, 2> : trpl_sim_cta_kernel<2, 8, 1>;
+        case 4: return c.pad ? trpl_sim_cta_kernel<4, 8, 2> : trpl_sim_cta_kernel<4, 8, 1>;
+        default: return c.pad ? trpl_sim_cta_kernel<8, 8, 2> : trpl_sim_cta_kernel<8, 8, 1>;
         }
     }
     switch (c.M) {
@@ -133,7 +124,8 @@ void cfg_shape(const Cfg &c, int *threads, int *sims_per_cta, size_t *smem)
     if (c.W > 1) {
         *threads = c.W * 32;
         *sims_per_cta = 1;
-        *smem = c.W * ring + (size_t)(2 * 3 * 32 * c.W + 2 * c.W * 4) * sizeof(double);
+        // + exchange buffer [2][2][32W], reduction scratch [2][W][4], interface-system planes [9][(32+16/W)W]
+        *smem = c.W * ring + (size_t)(2 * 2 * 32 * c.W + 2 * c.W * 4 + 9 * (32 + 16 / c.W) * c.W) * sizeof(double);
     } else {
         *threads = WARPS_PER_CTA * 32;
         *sims_per_cta = WARPS_PER_CTA;
@@ -234,7 +226,7 @@ const char *trpl_last_cuda_error(void) { return g_cuda_err; }
 int trpl_resident_sims(int device, int L)
 {
     Cfg cfg;
-    int rc = pick_cfg(L, 0, &cfg);
+    int rc = pick_cfg(L, &cfg);
     if (rc) return rc;
     DeviceGuard guard;
     rc = guard.enter(device);
@@ -257,7 +249,7 @@ int trpl_solve_pl(const double *d_matpar, int64_t S, int64_t ld_matpar, const do
         (pl_dtype != TRPL_F64 && pl_dtype != TRPL_F32))
         return TRPL_EINVAL;
     Cfg cfg;
-    int rc = pick_cfg(L, flags, &cfg);
+    int rc = pick_cfg(L, &cfg);
     if (rc) return rc;
     DeviceGuard guard;
     rc = guard.enter(device);
@@ -296,7 +288,7 @@ int trpl_solve_loglik(const double *d_x, int64_t S, int64_t ldx, int mag_col,
         return TRPL_EINVAL;
     if (C > TRPL_MAX_CURVES || E > TRPL_MAX_EXP) return TRPL_EUNSUPPORTED;
     Cfg cfg;
-    int rc = pick_cfg(L, flags, &cfg);
+    int rc = pick_cfg(L, &cfg);
     if (rc) return rc;
     DeviceGuard guard;
     rc = guard.enter(device);

@@ -17,10 +17,18 @@ namespace trpl {
 template <int W>
 struct Comm {
     int g;            // lane index within the simulation
-    double *xb;       // W > 1: exchange buffer [2][3][G] doubles
+    double *xb;       // W > 1: exchange buffer [2][XB_K][G] doubles
     double *red;      // W > 1: reduction scratch [2][W][4] doubles
     int phase;        // ping-pong selector of xb
     int rphase;       // ping-pong selector of red
+    double *sb;       // W > 1: interface-system planes [9][SB_STRIDE * W] doubles (tridiag_solve)
+    // Row r of the 32*W interface rows lives at slot(r): rows are dealt round-robin into W blocks of
+    // 32 (+ padding), so that the solver warp, which takes W CONSECUTIVE rows per lane, and the
+    // owning lanes, which touch one row each, both access shared memory without bank conflicts.
+    static constexpr int XB_K = 2;
+    static constexpr int SB_STRIDE = 32 + (W > 1 ? 16 / W : 0);
+    static constexpr int SB_PLANE = SB_STRIDE * W;
+    static __device__ __forceinline__ int slot(const int r) { return (r % W) * SB_STRIDE + r / W; }
 
     // K values from lane g-dm (-> vm) and lane g+dp (-> vp); out-of-range sources return the
     // caller's own value (always multiplied by an exact zero downstream).  For W > 1 the barrier
@@ -39,7 +47,8 @@ struct Comm {
             return true;
         } else {
             constexpr int G = 32 * W;
-            double *buf = xb + phase * (3 * G);
+            static_assert(K <= XB_K || W == 1, "exchange buffer too small");
+            double *buf = xb + phase * (XB_K * G);
 #pragma unroll
             for (int k = 0; k < K; k++) buf[k * G + g] = v[k];
             const bool any_busy = __syncthreads_or(busy) != 0;
@@ -82,8 +91,9 @@ struct Comm {
     }
     // stop rule errN < TOL and errP < TOL (pvSimPCR.py:213-216) with err = sum|res| / sum|b|, evaluated
     // division-free as z = sum(|res| - TOL*|b|) < 0 for both species (one 2-value butterfly).
-    __device__ __forceinline__ void stop_rule(const double zN, const double zP, bool &converged,
-                                              bool &nonfinite)
+    // W > 1: stop_post() leaves the warp totals in shared memory, the block barriers of the tridiagonal
+    // solve that follows publish them, stop_collect() adds them up -- no barrier of its own.
+    __device__ __forceinline__ double stop_butterfly(const double zN, const double zP)
     {
         const int lane = threadIdx.x & 31;
         const bool hi16 = (lane & 16) != 0;
@@ -94,16 +104,31 @@ struct Comm {
         k += __shfl_xor_sync(FULL, k, 4);
         k += __shfl_xor_sync(FULL, k, 2);
         k += __shfl_xor_sync(FULL, k, 1);
-        // lanes 0-15: zN of this warp, lanes 16-31: zP
-        if constexpr (W > 1) {
-            double *r = red + rphase * (W * 4);
-            if ((lane & 15) == 0) r[(threadIdx.x >> 5) * 4 + (lane >> 4)] = k;
-            __syncthreads();
-            k = 0.0;
+        return k;                 // lanes 0-15: zN of this warp, lanes 16-31: zP
+    }
+    __device__ __forceinline__ void stop_rule(const double zN, const double zP, bool &converged,
+                                              bool &nonfinite)
+    {
+        static_assert(W == 1, "multi-warp simulations use stop_post / stop_collect");
+        const double k = stop_butterfly(zN, zP);
+        converged = __all_sync(FULL, k < 0.0);
+        nonfinite = __any_sync(FULL, !(fabs(k) <= DBL_MAX));
+    }
+    __device__ __forceinline__ void stop_post(const double zN, const double zP)
+    {
+        const int lane = threadIdx.x & 31;
+        const double k = stop_butterfly(zN, zP);
+        double *r = red + rphase * (W * 4);
+        if ((lane & 15) == 0) r[(threadIdx.x >> 5) * 4 + (lane >> 4)] = k;
+    }
+    __device__ __forceinline__ void stop_collect(bool &converged, bool &nonfinite)
+    {
+        const int lane = threadIdx.x & 31;
+        const double *r = red + rphase * (W * 4);
+        double k = 0.0;
 #pragma unroll
-            for (int w = 0; w < W; w++) k += r[w * 4 + (lane >> 4)];
-            rphase ^= 1;
-        }
+        for (int w = 0; w < W; w++) k += r[w * 4 + (lane >> 4)];
+        rphase ^= 1;
         converged = __all_sync(FULL, k < 0.0);
         nonfinite = __any_sync(FULL, !(fabs(k) <= DBL_MAX));
     }
@@ -129,17 +154,29 @@ __device__ __forceinline__ void pcr_stage(double &Lr, double &Ur, double &Br, co
 // Rows outside the physical system must be identity rows (l=u=0, d=1).  l of the first row
 // and u of the last physical row must be 0.
 // Returns the new value of the previous lane's last node (needed by the callers anyway).
-template <int M, int W>
+//
+// W == 1: register-local partition sweep over the M-1 interior rows of every lane, then parallel cyclic
+// reduction over the 32 interface rows with warp shuffles.
+// W  > 1 (one CTA per simulation): the same lane-local sweep; the 32*W interface rows are then handed to
+// warp 0 through shared memory, which holds W of them per lane and solves them with the W == 1 code
+// (a second partition level + shuffle PCR): two block barriers per solve instead of one per PCR stage
+// over 32*W unknowns.  The neighbour values the caller needs (previous lane's last node, next lane's
+// first node) are rebuilt from the interface solution, so no further exchange follows the solve.
+// xr receives the new value of the NEXT lane's first node.
+// LAT = latency-optimised variant (multi-warp simulations run 2 warps per scheduler, so dependent
+// chains are exposed): pivot reciprocals from the leading minors, which are independent of each other,
+// instead of the Thomas recurrence (3 multiplies fewer, but M-1 reciprocals in series).
+template <int M, int W, bool LAT = (W > 1) && (TRPL_CTA_LAT != 0)>
 __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const double (&d)[M],
                                                 const double (&u)[M], const double (&b)[M],
-                                                double (&x)[M], Comm<W> &cm)
+                                                double (&x)[M], Comm<W> &cm, double &xr)
 {
     // [sec:partition]
     double Lr, Dr, Ur, Br;
     double c[M > 1 ? M - 1 : 1], y[M > 1 ? M - 1 : 1], v[M > 1 ? M - 1 : 1], w[M > 1 ? M - 1 : 1];
     if constexpr (M > 1) {
         // interior rows 0..M-2:  x_j = y_j - v_j * s_left - w_j * s_own
-#if TRPL_MINOR_PIVOTS
+        if constexpr (LAT || TRPL_MINOR_PIVOTS) {
         // Pivot reciprocals from the leading principal minors m_{j+1} = d_j m_j - l_j u_{j-1} m_{j-1}
         // (1/pivot_j = m_j / m_{j+1}): independent reciprocals, 3 more multiplies per solve.
         double ip[M - 1];
@@ -162,7 +199,7 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
             y[j] = fma(-l[j], y[j - 1], b[j]) * ip[j];
             v[j] = (-l[j] * v[j - 1]) * ip[j];
         }
-#else
+        } else {
         // Thomas forward sweep: pivot_j = d_j - l_j c_{j-1}
         {
             const double ip0 = rcp64(d[0]);
@@ -177,7 +214,7 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
             y[j] = fma(-l[j], y[j - 1], b[j]) * ipj;
             v[j] = (-l[j] * v[j - 1]) * ipj;
         }
-#endif
+        }
         w[M - 2] = c[M - 2];
 #pragma unroll
         for (int j = M - 3; j >= 0; j--) {
@@ -185,18 +222,78 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
             v[j] = fma(-c[j], v[j + 1], v[j]);
             w[j] = -c[j] * w[j + 1];
         }
-        // interface row (local M-1) couples s_left, s_own and the next lane's first interior row
-        double mine[3] = {y[0], v[0], w[0]}, nm[3], nx[3];
-        cm.template xchg<3, false, true>(mine, 1, 1, nm, nx);
-        const double y0n = nx[0], v0n = nx[1], w0n = nx[2];
-        const double lr = l[M - 1], ur = u[M - 1];
-        Lr = -lr * v[M - 2];
-        Dr = fma(-ur, v0n, fma(-lr, w[M - 2], d[M - 1]));
-        Ur = -ur * w0n;
-        Br = fma(-ur, y0n, fma(-lr, y[M - 2], b[M - 1]));
+        if constexpr (W > 1) {
+            // Shared-memory planes (rows at Comm::slot): 0-6 = input of the solver warp, written by every
+            // lane before barrier 1 and read by warp 0 only; 7-8 = output (interface solution z, and the
+            // next lane's first node xr), written by warp 0 before barrier 2 and read by every lane after
+            // it.  Inputs and outputs never share a plane, so one buffer is enough: the next solve's
+            // inputs are written after barrier 2 of this one, its outputs after its own barrier 1.
+            constexpr int G = 32 * W, PL_ = Comm<W>::SB_PLANE, ST_ = Comm<W>::SB_STRIDE;
+            const int g = cm.g;
+            double *sb = cm.sb;
+            const int me = Comm<W>::slot(g);
+            const double lr = l[M - 1];
+            sb[0 * PL_ + me] = y[0];
+            sb[1 * PL_ + me] = v[0];
+            sb[2 * PL_ + me] = w[0];
+            sb[3 * PL_ + me] = -lr * v[M - 2];                      // this lane's share of its interface row
+            sb[4 * PL_ + me] = fma(-lr, w[M - 2], d[M - 1]);
+            sb[5 * PL_ + me] = fma(-lr, y[M - 2], b[M - 1]);
+            sb[6 * PL_ + me] = u[M - 1];
+            __syncthreads();
+            if (g < 32) {
+                double L2[W], D2[W], U2[W], B2[W], Z[W];
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    const int r = W * g + k;                       // slot(r) = k * ST_ + g
+                    const int here = k * ST_ + g;
+                    const int next = (k + 1 < W) ? here + ST_ : ((g < 31) ? g + 1 : here);
+                    const double ur = (r < G - 1) ? sb[6 * PL_ + here] : 0.0;
+                    L2[k] = sb[3 * PL_ + here];
+                    D2[k] = fma(-ur, sb[1 * PL_ + next], sb[4 * PL_ + here]);
+                    U2[k] = -ur * sb[2 * PL_ + next];
+                    B2[k] = fma(-ur, sb[0 * PL_ + next], sb[5 * PL_ + here]);
+                }
+                Comm<1> c1;
+                c1.g = g; c1.xb = nullptr; c1.red = nullptr; c1.phase = 0; c1.rphase = 0; c1.sb = nullptr;
+                double znext;                                      // first row of the next lane
+                tridiag_solve<W, 1, (TRPL_CTA_LAT != 0)>(L2, D2, U2, B2, Z, c1, znext);
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    const int here = k * ST_ + g;
+                    const int next = (k + 1 < W) ? here + ST_ : ((g < 31) ? g + 1 : here);
+                    const double zn = (k + 1 < W) ? Z[k + 1] : znext;
+                    sb[7 * PL_ + here] = Z[k];
+                    sb[8 * PL_ + here] = fma(-sb[2 * PL_ + next], zn, fma(-sb[1 * PL_ + next], Z[k], sb[0 * PL_ + next]));
+                }
+            }
+            __syncthreads();
+            const double z = sb[7 * PL_ + me];
+            const double zl = (g > 0) ? sb[7 * PL_ + Comm<W>::slot(g - 1)] : 0.0;
+            xr = (g < G - 1) ? sb[8 * PL_ + me] : 0.0;
+            x[M - 1] = z;
+#pragma unroll
+            for (int j = 0; j < M - 1; j++) x[j] = fma(-w[j], z, fma(-v[j], zl, y[j]));
+            return zl;
+        }
+        if constexpr (W == 1) {
+            // interface row (local M-1) couples s_left, s_own and the next lane's first interior row
+            double mine[3] = {y[0], v[0], w[0]}, nm[3], nx[3];
+            cm.template xchg<3, false, true>(mine, 1, 1, nm, nx);
+            const double y0n = nx[0], v0n = nx[1], w0n = nx[2];
+            const double lr = l[M - 1], ur = u[M - 1];
+            Lr = -lr * v[M - 2];
+            Dr = fma(-ur, v0n, fma(-lr, w[M - 2], d[M - 1]));
+            Ur = -ur * w0n;
+            Br = fma(-ur, y0n, fma(-lr, y[M - 2], b[M - 1]));
+        }
     } else {
         Lr = l[0]; Dr = d[0]; Ur = u[0]; Br = b[0];
     }
+    static_assert(W == 1 || M > 1, "multi-warp simulations keep at least 2 nodes per lane");
+    if constexpr (W > 1) {
+        return 0.0;        // not reached: the multi-warp path returned above
+    } else {
     // [sec:normalise] parallel cyclic reduction over the 32*W interface unknowns, unit diagonal
     {
         double inv = rcp64(Dr);
@@ -204,7 +301,7 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
     }
     // [sec:pcr]
 #pragma unroll
-    for (int rf = 1; rf < 32 * W; rf <<= 1) {
+    for (int rf = 1; rf < 32; rf <<= 1) {
         // Off-diagonals shrink quadratically per stage.  Let m = max |L|,|U| over the simulation:
         //   m < 2^-70: the remaining stages cannot change D = 1 or B in the last bit: stop;
         //   m < 2^-35: this is the last stage, and in it D = 1 - O(m^2) rounds to exactly 1 and the new
@@ -215,24 +312,17 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
         const int hl = __double2hiint(Lr) & 0x7fffffff, hu = __double2hiint(Ur) & 0x7fffffff;
         const int hm = max(hl, hu);
         const bool busy = (rf < 8) || (hm >= ((1023 - TRPL_PCR_LAST_EXP) << 20));
-        if constexpr (W == 1) {
-            if (rf >= 8 && !__any_sync(FULL, busy)) {
-                if (__any_sync(FULL, hm >= ((1023 - 70) << 20))) {
-                    double mine[1] = {Br}, vm[1], vp[1];
-                    cm.template xchg<1, true, true>(mine, rf, rf, vm, vp);
-                    Br = fma(-vp[0], Ur, fma(-vm[0], Lr, Br));
-                }
-                break;
+        if (rf >= 8 && !__any_sync(FULL, busy)) {
+            if (__any_sync(FULL, hm >= ((1023 - 70) << 20))) {
+                double mine[1] = {Br}, vm[1], vp[1];
+                cm.template xchg<1, true, true>(mine, rf, rf, vm, vp);
+                Br = fma(-vp[0], Ur, fma(-vm[0], Lr, Br));
             }
-            double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
-            cm.template xchg<3, true, true>(mine, rf, rf, vm, vp);
-            pcr_stage(Lr, Ur, Br, vm, vp);
-        } else {
-            double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
-            const bool busy70 = (rf < 8) || (hm >= ((1023 - 70) << 20));
-            if (!cm.template xchg<3, true, true>(mine, rf, rf, vm, vp, busy70)) break;
-            pcr_stage(Lr, Ur, Br, vm, vp);
+            break;
         }
+        double mine[3] = {Lr, Ur, Br}, vm[3], vp[3];
+        cm.template xchg<3, true, true>(mine, rf, rf, vm, vp);
+        pcr_stage(Lr, Ur, Br, vm, vp);
     }
     // [sec:backsubst]
     x[M - 1] = Br;
@@ -241,7 +331,9 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
 #pragma unroll
         for (int j = 0; j < M - 1; j++) x[j] = fma(-w[j], Br, fma(-v[j], sl, y[j]));
     }
+    xr = cm.from_next(x[0]);
     return sl;
+    }   // W == 1
 }
 
 // [sec:none]
@@ -285,7 +377,14 @@ struct WarpScratch {      // per-warp shared scratch touched once every 32 PL sa
 // ---------------------------------------------------------------------------------------------
 // one (sample, curve) simulation, executed by W warps (W == 1: one warp; W > 1: one CTA)
 // ---------------------------------------------------------------------------------------------
-template <int M, bool PAD, int W>
+// PADM = how a grid that does not fill the 32*W*M node slots is handled:
+//   0  exact fit (L == 32*W*M);
+//   1  L is a multiple of M: the lanes beyond the last physical one carry an independent dummy film at
+//      equilibrium (N0, P0, E = 0, no excitation, no surface recombination, zero-flux ends).  It is
+//      cut off from the physical system exactly like the two film surfaces are (one missing-neighbour
+//      edge), it is left out of the residual norms and of PL, and it costs no per-row selects;
+//   2  any L: nodes beyond L-1 are identity rows (selects on every row).
+template <int M, int PADM, int W>
 __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long long s,
                                         double *ring_warp, WarpScratch *ws, const int lane,
                                         Comm<W> &cm)
@@ -358,14 +457,18 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
 
     // ---- geometry of this lane
     const int last_lane = (L - 1) / M;         // lane owning node L-1 ...
-    const int jl = PAD ? (L - 1) % M : M - 1;  // ... at local index jl (M-1 on exact-fit grids)
+    constexpr bool PAD = (PADM == 2);
+    const int jl = PAD ? (L - 1) % M : M - 1;  // ... at local index jl (M-1 unless PADM == 2)
+    const bool dummy = (PADM == 1) && (g > last_lane);   // lane of the dummy film
     bool ev[M + 1];                            // edge m = M*g + j is an interior edge (1..L-1)
 #pragma unroll
     for (int j = 0; j <= M; j++) {
         const int m = M * g + j;
         // exact-fit grids (L == M*G): only edge 0 (first lane) and edge L (last lane) are
         // boundaries, so the selects on the inner edges fold away at compile time
-        ev[j] = PAD ? ((m >= 1) && (m <= L - 1)) : (j == 0 ? (g != 0) : (j == M ? (g != G - 1) : true));
+        ev[j] = PAD ? ((m >= 1) && (m <= L - 1))
+                    : (j == 0 ? (g != 0 && !(PADM == 1 && g == last_lane + 1))
+                              : (j == M ? (g != G - 1 && !(PADM == 1 && g == last_lane)) : true));
     }
     bool nv[M];                                // node n = M*g + j exists
 #pragma unroll
@@ -511,6 +614,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             double part = 0.0;
 #pragma unroll
             for (int j = 0; j < M; j++) part = fma(N[j], P[j], part);
+            if (PADM == 1) part = dummy ? 0.0 : part;
             const double tot = cm.sum(part);
             const double plraw = rate * (tot + mLN0P0);
             if (lane == (pl_idx & 31)) keep = plraw;
@@ -534,7 +638,6 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             else if (order == 4) { a0 = 25.0 / 12; a1 = -4.0; a2 = 3.0; a3 = -4.0 / 3; a4 = 0.25; }
             else { a0 = 137.0 / 60; a1 = -5.0; a2 = 5.0; a3 = -10.0 / 3; a4 = 1.25; a5 = -0.2; }
         }
-        const double a0p2DN = fma(2.0, DN, a0), a0p2DP = fma(2.0, DP, a0);   // diagonal with both neighbours
 
         // ---- history sums bU = a1 U(t) + a2 U(t-1) + ... + a5 U(t-4)       (pvSimPCR.py:133-135)
         double bN[M], bP[M], bE[M];
@@ -565,6 +668,8 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             ring.store(slot, 1, P);
             ring.store(slot, 2, E);
         }
+        double bEn = 0.0;              // history sum of the next lane's first edge (W > 1 only)
+        if constexpr (W > 1) bEn = cm.from_next(bE[0]);
 
         // [sec:loop] ---- Newton / Gauss-Seidel iteration                   (pvSimPCR.py:147-216)
         int it = 0;
@@ -574,18 +679,15 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             double zN = 0.0, zP = 0.0;    // sum(|residual| - TOL*|b|): err < TOL  <=>  z < 0
             bool converged_now = false, nonfinite_now = false;
 
-            // Assembly notes (both species).  With e = E/2 on an edge the reference's rows are
-            //   l_j = D(+-e_j - 1),  u_j = D(-+e_{j+1} - 1),  d_j = a0 - u_{j-1} - l_{j+1} - ds
-            // (pvSimPCR.py:148-161,178-190), so d_j = a0 + 2D +- D(e_j - e_{j+1}) - ds: one FMA on the
-            // edge difference dE (shared by the two species).  A missing neighbour (front of node 0,
-            // back of node L-1: E = 0 there) takes one D off the diagonal and zeroes the off-diagonal;
-            // that correction rides on the surface-recombination rows, which touch the same two nodes.
-            // SRH: (P*tp - tauP*np)/tp^2 = (tauN*P^2 + tauP*N0P0)/tp^2 exactly, one product fewer and
-            // no cancellation.  -ds = P*(B + CP*P + 2*CN*N) + srh - CN*N0P0 (Auger terms regrouped so
-            // that CN*N, CP*P + CN*N and B + ... are shared with the rhs factor).
+            // Assembly notes (both species).  -ds = X*(B + CP*P + CN*N) + C_X*np + srh (X = the other
+            // species): the factor B + CP*P + CN*N is shared with the rhs, and no product of two
+            // per-simulation constants appears inside the loop (see ctab above).  With the constant table
+            // the SRH numerator P*tp - tauP*np is evaluated as the equal tauN*P^2 + tauP*N0P0 (one product
+            // fewer, no cancellation).
 
             // [sec:N-assembly] ======== N system (P, E frozen) ========
             {
+                double nds_[M];
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     const double Nj = N[j], Pj = P[j];
@@ -600,11 +702,35 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
 #endif
                     const double hr = fma(CP, Pj, CN * Nj) + rate;
                     const double nds = fma(Pj, hr, fma(CN, npp, qr * r));               // = -ds
-                    const double Ep = (j < M - 1) ? E[j + 1] : En;
-                    l[j] = fma(hDN, E[j], -DN);                                          // DN*(+E/2 - 1)
-                    u[j] = fma(-hDN, Ep, -DN);                                           // DN*(-E/2 - 1)
-                    d[j] = fma(hDN, E[j] - Ep, nds + a0p2DN);
+                    nds_[j] = nds;
                     b[j] = fma(nds, Nj, -fma(hr + r, npp, bN[j]));
+                }
+                // transport rows.  The diagonal takes exactly the rounded off-diagonals of the two
+                // neighbouring rows (d_j = a0 - u_{j-1} - l_{j+1} - ds, pvSimPCR.py:159): the column sums of
+                // the transport part vanish in floating point, i.e. the step conserves carriers to the
+                // last bit -- a diagonal rebuilt from E differences does not, and that noise ends up in
+                // PL = rate*(sum N*P - L*N0*P0) once the excess has decayed (measured: stiff-regime agreement
+                // with the CPU restatement 96.9 % -> 94.9 %, profiles/r02_variants.txt).
+                {
+                    const double cu0 = sel(ev[0], fma(-hDN, E[0], -DN), 0.0);      // u of the previous lane's last row
+                    const double clM = sel(ev[M], fma(hDN, En, -DN), 0.0);         // l of the next lane's first row
+#pragma unroll
+                    for (int j = 0; j < M; j++) {
+                        const double Ep = (j < M - 1) ? E[j + 1] : En;
+                        l[j] = fma(hDN, E[j], -DN);                                      // DN*(+E/2 - 1)
+                        u[j] = fma(-hDN, Ep, -DN);                                       // DN*(-E/2 - 1)
+                        if (PAD) {
+                            l[j] = sel(nv[j] && ev[j], l[j], 0.0);
+                            u[j] = sel(nv[j] && ev[j + 1], u[j], 0.0);
+                        }
+                    }
+                    if (!PAD) {
+                        l[0] = sel(ev[0], l[0], 0.0);
+                        u[M - 1] = sel(ev[M], u[M - 1], 0.0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < M; j++)
+                        d[j] = ((a0 - ((j == 0) ? cu0 : u[j - 1])) - ((j == M - 1) ? clM : l[j + 1])) + nds_[j];
                 }
                 // [sec:N-surface] surface recombination rows (pvSimPCR.py:164-170) + missing-neighbour fix
                 {
@@ -619,32 +745,26 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double srs = srf * rs;
                     const double nd = fma(Ps, Ps, N0P0) * (srs * rs);                   // = -ds0
                     const double db = fma(-nd, Ns, fma(Ns, Ps, -N0P0) * srs);
-                    const double ndm = nd - DN;
                     if (PAD) {
 #pragma unroll
                         for (int j = 0; j < M; j++) {
                             const bool at = (is_first && j == 0) || (is_last && j == jl);
-                            d[j] += at ? ndm : 0.0;
+                            d[j] += at ? nd : 0.0;
                             b[j] -= at ? db : 0.0;
                         }
                     } else {
-                        d[0] += is_first ? ndm : 0.0;
+                        d[0] += is_first ? nd : 0.0;
                         b[0] -= is_first ? db : 0.0;
-                        d[M - 1] += is_last ? ndm : 0.0;
+                        d[M - 1] += is_last ? nd : 0.0;
                         b[M - 1] -= is_last ? db : 0.0;
                     }
                 }
                 if (PAD) {
 #pragma unroll
                     for (int j = 0; j < M; j++) {
-                        l[j] = sel(nv[j] && ev[j], l[j], 0.0);
-                        u[j] = sel(nv[j] && ev[j + 1], u[j], 0.0);
                         d[j] = sel(nv[j], d[j], 1.0);
                         b[j] = sel(nv[j], b[j], 0.0);
                     }
-                } else {
-                    l[0] = sel(is_first, 0.0, l[0]);
-                    u[M - 1] = sel(is_last, 0.0, u[M - 1]);
                 }
                 // [sec:N-residual] L1 residual of the current iterate         (pvSimPCR.py:172, :14-40)
 #pragma unroll
@@ -654,14 +774,14 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double res = fma(l[j], xm, fma(d[j], N[j], fma(u[j], xp, -b[j])));
                     zN = fma(-TOL, fabs(b[j]), zN + fabs(res));
                 }
+                if (PADM == 1) zN = dummy ? 0.0 : zN;
                 // [sec:N-solve]
-                Nl = tridiag_solve<M, W>(l, d, u, b, N, cm);
-                // [sec:N-exchange]
-                Nr = cm.from_next(N[0]);
+                Nl = tridiag_solve<M, W>(l, d, u, b, N, cm, Nr);
             }
 
             // [sec:P-assembly] ======== P system (new N) ========
             {
+                double nds_[M];
 #pragma unroll
                 for (int j = 0; j < M; j++) {
                     const double Nj = N[j], Pj = P[j];
@@ -676,11 +796,29 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
 #endif
                     const double hr = fma(CN, Nj, CP * Pj) + rate;
                     const double nds = fma(Nj, hr, fma(CP, npp, qr * r));
-                    const double Ep = (j < M - 1) ? E[j + 1] : En;
-                    l[j] = fma(-hDP, E[j], -DP);                                         // DP*(-E/2 - 1)
-                    u[j] = fma(hDP, Ep, -DP);                                            // DP*(+E/2 - 1)
-                    d[j] = fma(-hDP, E[j] - Ep, nds + a0p2DP);
+                    nds_[j] = nds;
                     b[j] = fma(nds, Pj, -fma(hr + r, npp, bP[j]));
+                }
+                {
+                    const double cu0 = sel(ev[0], fma(hDP, E[0], -DP), 0.0);
+                    const double clM = sel(ev[M], fma(-hDP, En, -DP), 0.0);
+#pragma unroll
+                    for (int j = 0; j < M; j++) {
+                        const double Ep = (j < M - 1) ? E[j + 1] : En;
+                        l[j] = fma(-hDP, E[j], -DP);                                     // DP*(-E/2 - 1)
+                        u[j] = fma(hDP, Ep, -DP);                                        // DP*(+E/2 - 1)
+                        if (PAD) {
+                            l[j] = sel(nv[j] && ev[j], l[j], 0.0);
+                            u[j] = sel(nv[j] && ev[j + 1], u[j], 0.0);
+                        }
+                    }
+                    if (!PAD) {
+                        l[0] = sel(ev[0], l[0], 0.0);
+                        u[M - 1] = sel(ev[M], u[M - 1], 0.0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < M; j++)
+                        d[j] = ((a0 - ((j == 0) ? cu0 : u[j - 1])) - ((j == M - 1) ? clM : l[j + 1])) + nds_[j];
                 }
                 // [sec:P-surface]
                 {
@@ -695,32 +833,26 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                     const double srs = srf * rs;
                     const double nd = fma(Ns, Ns, N0P0) * (srs * rs);
                     const double db = fma(-nd, Ps, fma(Ns, Ps, -N0P0) * srs);
-                    const double ndm = nd - DP;
                     if (PAD) {
 #pragma unroll
                         for (int j = 0; j < M; j++) {
                             const bool at = (is_first && j == 0) || (is_last && j == jl);
-                            d[j] += at ? ndm : 0.0;
+                            d[j] += at ? nd : 0.0;
                             b[j] -= at ? db : 0.0;
                         }
                     } else {
-                        d[0] += is_first ? ndm : 0.0;
+                        d[0] += is_first ? nd : 0.0;
                         b[0] -= is_first ? db : 0.0;
-                        d[M - 1] += is_last ? ndm : 0.0;
+                        d[M - 1] += is_last ? nd : 0.0;
                         b[M - 1] -= is_last ? db : 0.0;
                     }
                 }
                 if (PAD) {
 #pragma unroll
                     for (int j = 0; j < M; j++) {
-                        l[j] = sel(nv[j] && ev[j], l[j], 0.0);
-                        u[j] = sel(nv[j] && ev[j + 1], u[j], 0.0);
                         d[j] = sel(nv[j], d[j], 1.0);
                         b[j] = sel(nv[j], b[j], 0.0);
                     }
-                } else {
-                    l[0] = sel(is_first, 0.0, l[0]);
-                    u[M - 1] = sel(is_last, 0.0, u[M - 1]);
                 }
                 // [sec:P-residual]
 #pragma unroll
@@ -733,11 +865,12 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 // [sec:stop-rule] ---- stop decision for THIS iteration (pvSimPCR.py:213-216): both L1
                 // residuals are known here, before the P solve; reducing them now lets the shuffle
                 // chain overlap the solve.
-                cm.stop_rule(zN, zP, converged_now, nonfinite_now);
+                if (PADM == 1) zP = dummy ? 0.0 : zP;
+                if constexpr (W == 1) cm.stop_rule(zN, zP, converged_now, nonfinite_now);
+                else cm.stop_post(zN, zP);
                 // [sec:P-solve]
-                Pl = tridiag_solve<M, W>(l, d, u, b, P, cm);
-                // [sec:P-exchange]
-                Pr = cm.from_next(P[0]);
+                Pl = tridiag_solve<M, W>(l, d, u, b, P, cm, Pr);
+                if constexpr (W > 1) cm.stop_collect(converged_now, nonfinite_now);
             }
 
             // [sec:E-update] ======== E update on interior edges             (pvSimPCR.py:205-209)
@@ -749,7 +882,15 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 const double num = fma(LamDP, P[j] - Pm, fma(-LamDN, N[j] - Nm, -bE[j]));
                 E[j] = sel(ev[j], num * rcp64(den), 0.0);
             }
-            En = sel(ev[M], cm.from_next(E[0]), 0.0);      // no edge beyond the back surface
+            if constexpr (W == 1) {
+                En = sel(ev[M], cm.from_next(E[0]), 0.0);      // no edge beyond the back surface
+            } else {
+                // the next lane's first edge from values this lane already holds (bit-identical to what
+                // the owner computes): saves a block barrier per iteration
+                const double den = fma(hLamDP, Pr + P[M - 1], fma(hLamDN, Nr + N[M - 1], a0));
+                const double num = fma(LamDP, Pr - P[M - 1], fma(-LamDN, Nr - N[M - 1], -bEn));
+                En = sel(ev[M], num * rcp64(den), 0.0);
+            }
 
             // [sec:loop] ======== stop rule (pvSimPCR.py:213-216): decided by the flags computed before the P solve
             it++;
@@ -807,7 +948,7 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
     double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32);
     const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
     Comm<1> cm;
-    cm.g = lane; cm.xb = nullptr; cm.red = nullptr; cm.phase = 0; cm.rphase = 0;
+    cm.g = lane; cm.xb = nullptr; cm.red = nullptr; cm.phase = 0; cm.rphase = 0; cm.sb = nullptr;
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(a.counter, 1ULL);
@@ -816,13 +957,14 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
         // items are issued curve-major, longest curve first, so short ones fill the tail of the launch
         const int c = a.curve_order[(int)(item / (unsigned long long)a.S)];
         const long long s = (long long)(item % (unsigned long long)a.S);
-        run_sim<M, PAD, 1>(a, c, s, ring_warp, &scratch[warp], lane, cm);
+        run_sim<M, PAD ? 2 : 0, 1>(a, c, s, ring_warp, &scratch[warp], lane, cm);
     }
 }
 
-// Fine grids: one CTA of W warps per simulation, M nodes per lane (L <= 32*M*W).
-template <int W, int M>
-__global__ void __launch_bounds__(W * 32, (M == 4) ? 16 / W : 1)
+// Fine grids: one CTA of W warps per simulation, M nodes per lane (L <= 32*M*W); PADM as in run_sim
+// (1: L % M == 0, 2: any L).
+template <int W, int M, int PADM>
+__global__ void __launch_bounds__(W * 32, 1)
 trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -833,7 +975,8 @@ trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
     Comm<W> cm;
     cm.g = threadIdx.x;
     cm.xb = smem + (size_t)W * (4 * 3 * M * 32);
-    cm.red = cm.xb + 2 * 3 * 32 * W;
+    cm.red = cm.xb + 2 * Comm<W>::XB_K * 32 * W;
+    cm.sb = cm.red + 2 * W * 4;
     cm.phase = 0; cm.rphase = 0;
     const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
     for (;;) {
@@ -844,7 +987,7 @@ trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
         if (item >= total) break;
         const int c = a.curve_order[(int)(item / (unsigned long long)a.S)];
         const long long s = (long long)(item % (unsigned long long)a.S);
-        run_sim<M, true, W>(a, c, s, ring_warp, &scratch, lane, cm);
+        run_sim<M, PADM, W>(a, c, s, ring_warp, &scratch, lane, cm);
     }
 }
 

@@ -62,7 +62,6 @@ extern "C" {
 #define TRPL_F_LOG_PL          2   /* compare log10(PL)      (sim_flags["log_pl"],         bayeslib.py:155)    */
 #define TRPL_F_SELF_NORMALIZE  4   /* PL /= PL[t=0]          (sim_flags["self_normalize"], bayeslib.py:150)    */
 #define TRPL_F_EMULATE_F32     8   /* reproduce the float32 PL buffer of bayeslib.py:137 (store, /=, log10f)   */
-#define TRPL_F_FINE_M4        16   /* fine grids (L > 256): 4 nodes per lane instead of 8 (A/B testing only)   */
 
 /* One observation set (one curve of one observation file), device arrays of length n.
  * Produced by trpl_obs_prepare + upload.  Observation i is compared with

@@ -79,7 +79,7 @@ def route_a_case(inis, S=256, T=4000, truth_pl=None):
     grid = np.linspace(0, Time, T + 1)
     e_t, e_v, e_u = [], [], []
     for c in range(3):
-        n = [1501, 2201, 3001][c]
+        n = min([1501, 2201, 3001][c], (T * 3) // 4 + 1)
         tt = np.linspace(0, grid[n - 1], n)
         if c == 2:
             tt = tt[:-1] + 0.3 * 0.025          # off-grid

@@ -152,7 +152,7 @@ def test_pvsim_matches_reference_numba_kernels_live():
         assert ex.max() <= 1.0, "curve %d: worst excess %.3g" % (c, ex.max())
         # likelihood of every sample whose curve stays clear of the cancellation floor, evaluated the
         # same way on both sides (f64 log10, residual against the truth sample's reference curve)
-        clean = (np.abs(ref) > 1e4 * floor[:, None]).all(axis=1)
+        clean = (np.abs(ref) > 1e6 * floor[:, None]).all(axis=1)
         assert clean.mean() > 0.5
         lr, lm = np.log10(ref[clean]), np.log10(pl[clean])
         tgt = np.log10(ref[0])
@@ -173,11 +173,6 @@ def test_reference_bayeslib_drives_the_dropins_live():
     T = 2000
     case = route_a_case(inis, 96, T, truth_pl=lambda c: oracle.solve(
         (TRUTH * UC)[None, :12], [2000.0, 0.025 * T, 128, T, 1, (0,), 7, 10000], inis[c], solver="thomas")["pl"][0])
-    # shorten the windows to this T
-    e_t, e_v, e_u = case["e_data"][0]
-    for c in range(3):
-        keep = e_t[c] <= 0.025 * T
-        e_t[c], e_v[c], e_u[c] = e_t[c][keep], e_v[c][keep], e_u[c][keep]
     args = (case["lo"], case["hi"], case["do_log"], inis, case["simPar"], case["e_data"], case["flags"], case["info"])
     N1, P1, X1 = rr.ref_bayes("reference", *args)
     N2, P2, X2 = rr.ref_bayes("dropin", *args)
