@@ -89,8 +89,12 @@ for a, s, _ in ins:
         m = re.search(r"`\((\.L_x_\d+)\)", s)
         if m and m.group(1) in addr_of_label and addr_of_label[m.group(1)] <= a:
             loops.append((addr_of_label[m.group(1)], a))
-cands = [(lo, hi) for lo, hi in loops if 400 <= sum(1 for a, _, _ in ins if lo <= a <= hi) <= 1600]
-lo, hi = sorted(cands, key=lambda c: c[1] - c[0])[0]
+LO_, HI_ = (int(os.environ.get("LOOP_MIN", 400)), int(os.environ.get("LOOP_MAX", 1600)))
+cands = [(lo, hi) for lo, hi in loops if LO_ <= sum(1 for a, _, _ in ins if lo <= a <= hi) <= HI_]
+def _fp64_frac(c):
+    body_ = [s_ for a_, s_, _ in ins if c[0] <= a_ <= c[1]]
+    return sum(1 for s_ in body_ if op(s_) in ("DFMA", "DMUL", "DADD")) / float(len(body_))
+lo, hi = sorted(cands, key=_fp64_frac)[-1]          # the Newton loop is the FP64-densest big loop
 body = [(a, s, c) for a, s, c in ins if lo <= a <= hi]
 
 

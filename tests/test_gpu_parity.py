@@ -43,7 +43,7 @@ def _assert_pl_close(pl, ref, mat, simPar, rtol=1e-6):
 # forward model: reference goldens (tiny shapes the numba simulator can run)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["pvsim_points_f64", "pvsim_points_f32", "pvsim_exp_f64",
-                                  "pvsim_stiff_f64", "pvsim_L32_f64", "pvsim_L128_f64"])
+                                  "pvsim_stiff_f64", "pvsim_L32_f64", "pvsim_L128_f64", "pvsim_long_f64"])
 def test_pvsim_dropin_matches_reference_golden(trpl, name):
     path = os.path.join(GOLDEN, "cudasim_%s.npz" % name)
     if not os.path.exists(path):

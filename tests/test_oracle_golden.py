@@ -28,7 +28,7 @@ def _solve_like_golden(g, solver, simulator_pow=False):
 
 
 @pytest.mark.parametrize("name", ["pvsim_points_f64", "pvsim_points_f32", "pvsim_exp_f64",
-                                  "pvsim_stiff_f64", "pvsim_L32_f64", "pvsim_L128_f64"])
+                                  "pvsim_stiff_f64", "pvsim_L32_f64", "pvsim_L128_f64", "pvsim_long_f64"])
 def test_pcr_oracle_is_bit_exact_with_reference_kernels(name):
     path = os.path.join(GOLDEN, "cudasim_%s.npz" % name)
     if not os.path.exists(path):
@@ -43,7 +43,8 @@ def test_pcr_oracle_is_bit_exact_with_reference_kernels(name):
     np.testing.assert_allclose(pl2, g["pl"], rtol=1e-13 if pl2.dtype == np.float64 else 0)
 
 
-@pytest.mark.parametrize("name", ["pvsim_points_f64", "pvsim_exp_f64", "pvsim_stiff_f64", "pvsim_L32_f64", "pvsim_L128_f64"])
+@pytest.mark.parametrize("name", ["pvsim_points_f64", "pvsim_exp_f64", "pvsim_stiff_f64", "pvsim_L32_f64", "pvsim_L128_f64",
+                                  "pvsim_long_f64"])
 def test_thomas_oracle_matches_reference_kernels(name):
     path = os.path.join(GOLDEN, "cudasim_%s.npz" % name)
     if not os.path.exists(path):
