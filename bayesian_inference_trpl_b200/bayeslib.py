@@ -116,16 +116,15 @@ def simulate(model, e_data, P, X, plI, plI_int, num_curves, sim_params, init_par
         # host -> pinned staging -> device, result device -> pinned -> P: one copy each way per call
         xh = engine.pinned("X", Xrows.shape, torch.float64)
         xh.numpy()[...] = Xrows
-        Xd = xh.to(dev, non_blocking=True)
-        torch.cuda.synchronize(dev)
         clock0 = time.perf_counter()
+        Xd = xh.to(dev, non_blocking=True)
         lnl, status, _ = engine.solve_loglik(Xd, problem, log_pl=log_pl, self_normalize=normalize,
                                              emulate_f32=gpu_info.get("emulate_f32", False))
         lh = engine.pinned("lnl", lnl.shape, torch.float64)
         sh = engine.pinned("status", status.shape, torch.int32)
         lh.copy_(lnl, non_blocking=True)
         sh.copy_(status, non_blocking=True)
-        torch.cuda.synchronize(dev)
+        engine.host_wait(dev)
         solver_time[gpu_id] += time.perf_counter() - clock0
         P[:, rows] += lh.numpy()
         bad = int(np.count_nonzero(sh.numpy()))

@@ -6,6 +6,7 @@ Shapes follow the reference: simPar = [Length, Time, L, T, plT, pT, tol, MAX]
 e_data = [(t_list, logPL_list, unc_list)] per observation file (bayes_io.py:99-102).
 """
 import ctypes
+import time
 
 import numpy as np
 import torch
@@ -33,6 +34,18 @@ def _row_stride(t):
 
 def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def host_wait(dev=None):
+    """Block the calling host thread until everything queued on the current stream has finished, by
+    polling an event.  The driver's blocking waits (cudaDeviceSynchronize / cudaStreamSynchronize /
+    cudaEventSynchronize, i.e. torch.cuda.synchronize and tensor.cpu()) were measured to return up to
+    0.7 s late after a multi-second kernel on the B200 boxes of this pool (tools/sync_latency.py,
+    profiles/r02_sync_latency.txt); polling learns of completion within 0.1 ms."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    while not ev.query():
+        time.sleep(0)           # yield the GIL / the core to other host threads between polls
 
 
 def to_device_f64(a, dev):

@@ -44,12 +44,12 @@ def pvSim(plI_main, plN_main, plP_main, plE_main, matPar, simPar, iniPar, TPB, B
         raise TypeError("plI_main must be float32 or float64")
     if plI_main.shape != (mat.shape[0], T // plT + 1):
         raise ValueError("plI_main must have shape (len(matPar), T//plT+1)")
-    torch.cuda.synchronize(dev)
+    engine.host_wait(dev)
     clock0 = time.time()
     pl, status, _ = engine.solve_pl(mat, init, float(Length), float(Time), L, T, plT, int(tol),
                                     int(MAX), out_dtype=odt, init_grid_units=grid_units,
                                     want_iters=False)
-    torch.cuda.synchronize(dev)
+    engine.host_wait(dev)
     solver_time = time.time() - clock0
     plI_main[:] = pl.cpu().numpy()
     if status_out is not None:

@@ -28,7 +28,17 @@ def resident():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); trpl.engine.solve_loglik(Xd, prob); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)
+_orig = trpl.engine.solve_loglik
+_ev = []
+def _timed(*a, **k):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); r = _orig(*a, **k); e1.record(); _ev.append((e0, e1)); return r
+trpl.engine.solve_loglik = _timed
 e2e(); resident()
+print("sequence test: e2e x3 then resident x3 then alternating")
+for f in (e2e, e2e, e2e, resident, resident, resident):
+    _ev.clear(); t0 = time.perf_counter(); f(); torch.cuda.synchronize(); w = time.perf_counter() - t0
+    print("  %-9s wall %.2f ms, kernel (events) %.2f ms" % (f.__name__, 1e3 * w, _ev[-1][0].elapsed_time(_ev[-1][1])))
 for rep in range(3):
     t0 = time.perf_counter(); inner = e2e(); torch.cuda.synchronize(); w = time.perf_counter() - t0
     r = resident()
