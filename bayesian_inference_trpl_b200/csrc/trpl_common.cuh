@@ -6,6 +6,7 @@
 #include <math.h>
 #include <float.h>
 #include <limits.h>
+#include <stdio.h>
 
 #include "trpl_b200.h"
 
@@ -30,6 +31,29 @@ constexpr int WARPS_PER_CTA = 4;
 #ifndef TRPL_PCR_LAST_EXP
 #define TRPL_PCR_LAST_EXP 35       // off-diagonals below 2^-this: the PCR stage degenerates to a B-only update
 #endif
+
+// -DTRPL_DEBUG=1: the sanitizer substitute (compute-sanitizer is closed on the pool this was developed on):
+// device-side bounds checks on every ring slot, observation index and exchange-buffer row, and a canary
+// word behind each warp's ring that is verified after every simulation.  A violation prints the site and
+// traps, which surfaces as TRPL_ECUDA on the host.  tests: run the GPU suite with TRPL_LIB pointing at the
+// debug build (tools/build_variants.py debug:-DTRPL_DEBUG=1; log in profiles/r02_debug_build_suite.txt).
+#ifndef TRPL_DEBUG
+#define TRPL_DEBUG 0
+#endif
+#if TRPL_DEBUG
+#define TRPL_DASSERT(cond)                                                                      \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            printf("TRPL_DEBUG violation %s at %s:%d (block %d thread %d)\n", #cond, __FILE__, \
+                   __LINE__, (int)blockIdx.x, (int)threadIdx.x);                                \
+            __trap();                                                                           \
+        }                                                                                       \
+    } while (0)
+#else
+#define TRPL_DASSERT(cond) do { } while (0)
+#endif
+constexpr int RING_CANARY = TRPL_DEBUG ? 2 : 0;        // doubles appended to each warp's ring
+constexpr unsigned long long CANARY_WORD = 0x5452504C43414E41ULL;   // "TRPLCANA"
 
 struct ObsDev {
     int n;

@@ -120,7 +120,7 @@ kern_t pick_kernel(const Cfg &c)
 // threads per CTA, simulations per CTA and dynamic shared memory of a configuration
 void cfg_shape(const Cfg &c, int *threads, int *sims_per_cta, size_t *smem)
 {
-    const size_t ring = (size_t)4 * 3 * c.M * 32 * sizeof(double);       // per warp
+    const size_t ring = (size_t)(4 * 3 * c.M * 32 + RING_CANARY) * sizeof(double);       // per warp
     if (c.W > 1) {
         *threads = c.W * 32;
         *sims_per_cta = 1;
@@ -207,7 +207,7 @@ int launch_sims(KArgs &ka, const Cfg &cfg, int device, cudaStream_t st)
 // =============================================================================================
 extern "C" {
 
-int trpl_version(void) { return 100; }
+int trpl_version(void) { return 200 + (TRPL_DEBUG ? 1 : 0); }   // odd = debug build (device-side checks)
 
 const char *trpl_error_string(int code)
 {

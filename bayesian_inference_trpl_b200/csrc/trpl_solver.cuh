@@ -54,6 +54,7 @@ struct Comm {
             const bool any_busy = __syncthreads_or(busy) != 0;
             const int im = (g - dm >= 0) ? g - dm : g;
             const int ip = (g + dp < G) ? g + dp : g;
+            TRPL_DASSERT(g >= 0 && g < G && im >= 0 && im < G && ip >= 0 && ip < G);
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 if (WANT_M) vm[k] = buf[k * G + im];
@@ -232,6 +233,7 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
             const int g = cm.g;
             double *sb = cm.sb;
             const int me = Comm<W>::slot(g);
+            TRPL_DASSERT(me >= 0 && me < PL_ && g < G);
             const double lr = l[M - 1];
             sb[0 * PL_ + me] = y[0];
             sb[1 * PL_ + me] = v[0];
@@ -344,6 +346,7 @@ struct Ring {
     // element (slot, field, j): chunks of 2 doubles per lane keep 16-byte accesses conflict-free
     __device__ __forceinline__ void load(int slot, int field, double (&h)[M]) const
     {
+        TRPL_DASSERT(slot >= 0 && slot < 4 && field >= 0 && field < 3);
         if constexpr (M == 1) {
             h[0] = base[(slot * 3 + field) * 32];
         } else {
@@ -358,6 +361,7 @@ struct Ring {
     }
     __device__ __forceinline__ void store(int slot, int field, const double (&h)[M]) const
     {
+        TRPL_DASSERT(slot >= 0 && slot < 4 && field >= 0 && field < 3);
         if constexpr (M == 1) {
             base[(slot * 3 + field) * 32] = h[0];
         } else {
@@ -569,6 +573,8 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
                 const bool mine = h < idx0 + cnt;
                 const unsigned bm = __ballot_sync(FULL, mine);
                 if (bm == 0u) break;
+                TRPL_DASSERT(pos >= 0 && pos <= ob.n);
+                TRPL_DASSERT(!mine || (h - idx0 >= 0 && h - idx0 < cnt && h >= 1));
                 const int shi = mine ? h - idx0 : 0;       // 0..cnt-1
                 const int slo = shi - 1;                   // -1..cnt-2
                 const double y_hi = __shfl_sync(FULL, lp, shi & 31);
@@ -945,7 +951,8 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
     extern __shared__ __align__(16) double smem[];
     __shared__ WarpScratch scratch[WARPS_PER_CTA];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32);
+    double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32 + RING_CANARY);
+    if (TRPL_DEBUG && lane == 0) reinterpret_cast<unsigned long long *>(ring_warp + 4 * 3 * M * 32)[0] = CANARY_WORD;
     const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
     Comm<1> cm;
     cm.g = lane; cm.xb = nullptr; cm.red = nullptr; cm.phase = 0; cm.rphase = 0; cm.sb = nullptr;
@@ -958,6 +965,7 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
         const int c = a.curve_order[(int)(item / (unsigned long long)a.S)];
         const long long s = (long long)(item % (unsigned long long)a.S);
         run_sim<M, PAD ? 2 : 0, 1>(a, c, s, ring_warp, &scratch[warp], lane, cm);
+        if (TRPL_DEBUG) TRPL_DASSERT(reinterpret_cast<unsigned long long *>(ring_warp + 4 * 3 * M * 32)[0] == CANARY_WORD);
     }
 }
 
@@ -971,10 +979,11 @@ trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
     __shared__ WarpScratch scratch;
     __shared__ unsigned long long next_item;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32);
+    double *ring_warp = smem + (size_t)warp * (4 * 3 * M * 32 + RING_CANARY);
+    if (TRPL_DEBUG && lane == 0) reinterpret_cast<unsigned long long *>(ring_warp + 4 * 3 * M * 32)[0] = CANARY_WORD;
     Comm<W> cm;
     cm.g = threadIdx.x;
-    cm.xb = smem + (size_t)W * (4 * 3 * M * 32);
+    cm.xb = smem + (size_t)W * (4 * 3 * M * 32 + RING_CANARY);
     cm.red = cm.xb + 2 * Comm<W>::XB_K * 32 * W;
     cm.sb = cm.red + 2 * W * 4;
     cm.phase = 0; cm.rphase = 0;
@@ -988,6 +997,7 @@ trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
         const int c = a.curve_order[(int)(item / (unsigned long long)a.S)];
         const long long s = (long long)(item % (unsigned long long)a.S);
         run_sim<M, PADM, W>(a, c, s, ring_warp, &scratch, lane, cm);
+        if (TRPL_DEBUG) TRPL_DASSERT(reinterpret_cast<unsigned long long *>(ring_warp + 4 * 3 * M * 32)[0] == CANARY_WORD);
     }
 }
 

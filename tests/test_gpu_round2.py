@@ -149,3 +149,22 @@ def test_calls_leave_the_callers_current_device_alone(trpl):
     assert torch.cuda.current_device() == 0
     y = torch.ones(8, device="cuda")
     assert y.device.index == 0
+
+
+def test_export_straight_from_device_buffers(trpl, tmp_path):
+    """SURVEY 8(f)-4: BAYRAN_P / BAYRAN_X written from CUDA tensors through a pinned staging chunk;
+    np.load (what the reference's GUI does, marginalization_visual.py) reads them back bit for bit."""
+    X = trpl.engine.random_grid_device(np.full(13, 1.0), np.full(13, 2.0), np.zeros(13, dtype=np.int32), 70001, 5)
+    P = -X[:, 0].contiguous() * 3.0
+    out = str(tmp_path / "DEV")
+    trpl.bayes_io.export_from_device(out, P, X, chunk_rows=4096)
+    np.testing.assert_array_equal(np.load(os.path.join(out, "DEV_BAYRAN_P.npy")), P.cpu().numpy())
+    np.testing.assert_array_equal(np.load(os.path.join(out, "DEV_BAYRAN_X.npy")), X.cpu().numpy())
+
+
+def test_debug_build_reports_itself(trpl):
+    """The library built with -DTRPL_DEBUG=1 (device-side bounds checks + ring canaries) has an odd version."""
+    v = trpl._lib.lib().trpl_version()
+    assert v >= 200
+    if "debug" in os.path.basename(trpl._lib.LIB_PATH):
+        assert v % 2 == 1

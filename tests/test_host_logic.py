@@ -261,3 +261,31 @@ def test_merge_task_exports(tmp_path):
     np.testing.assert_array_equal(Xm, X)
     base = os.path.basename(out)
     np.testing.assert_array_equal(np.load(os.path.join(out, base + "_BAYRAN_P.npy")), P)
+
+
+def test_vectorised_observation_reader_handles_the_reference_format_corners(tmp_path):
+    """One-pass reader: END row, blank lines, CRLF, a return to t=0 starts a new curve, ragged rows."""
+    from bayesian_inference_trpl_b200 import bayes_io
+    p = tmp_path / "o.csv"
+    p.write_text("0,1.5E+20,1E14\r\n0.025,1.25E+20,1E14\r\n\r\n0.05,1.0E+20,1E14\n0,3E+19,1E14\n0.025,2E+19,1E14\nEND\n9,9,9\n")
+    e = bayes_io.get_data([str(p)], {"time_cutoff": None, "select_obs_sets": None, "noise_level": None},
+                          {"log_pl": False, "self_normalize": False}, scale_f=1.0)[0]
+    assert [len(t) for t in e[0]] == [3, 2]
+    np.testing.assert_array_equal(e[0][0], [0, 0.025, 0.05])
+    np.testing.assert_array_equal(e[1][1], [3e19, 2e19])
+    q = tmp_path / "ragged.csv"
+    q.write_text("0,1,2,extra\n1,3,4\nEND\n")
+    e = bayes_io.get_data([str(q)], {"time_cutoff": None, "select_obs_sets": None, "noise_level": None},
+                          {"log_pl": False, "self_normalize": False}, scale_f=1.0)[0]
+    np.testing.assert_array_equal(e[1][0], [1, 3])
+
+
+def test_export_from_device_writes_valid_npy_on_cpu_tensors(tmp_path):
+    import torch
+    from bayesian_inference_trpl_b200 import bayes_io
+    P = torch.arange(1000, dtype=torch.float64) * -0.5
+    X = torch.arange(13000, dtype=torch.float64).reshape(1000, 13)
+    out = str(tmp_path / "DEV")
+    bayes_io.export_from_device(out, P, X, chunk_rows=128)
+    np.testing.assert_array_equal(np.load(os.path.join(out, "DEV_BAYRAN_P.npy")), P.numpy())
+    np.testing.assert_array_equal(np.load(os.path.join(out, "DEV_BAYRAN_X.npy")), X.numpy())
