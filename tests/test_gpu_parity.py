@@ -640,6 +640,15 @@ assert abs(float(lse) - ref) < 1e-10 * abs(ref)
 w = trpl.posterior.normalize(loc[0].contiguous())
 tot = w.sum(); dist.all_reduce(tot)
 assert abs(float(tot) - 1.0) < 1e-12
+# Philox sampler on the product path: every rank draws only its own rows on its GPU, tables gathered at the end
+pf = dict(flags, sampler="philox", seed=11, num_points=41)
+Nq, Pq, Xq = trpl.bayeslib.bayes(trpl.pvSim, np.array([0]), None, lo, hi, DO_LOG, inis, list(simPar), e_data, pf,
+                                 {"sims_per_gpu": 5, "num_gpus": world, "has_GPU": True})
+Xall = trpl.engine.random_grid_device(lo, hi, DO_LOG, 41, 11)
+assert np.array_equal(Xq, Xall.cpu().numpy()), "shards do not concatenate to the single-rank draw"
+prob = trpl.engine.Problem(simPar, inis, e_data, device=rank)
+ref_l, st, _ = trpl.engine.solve_loglik(Xall, prob)
+assert np.allclose(Pq, ref_l.cpu().numpy(), rtol=1e-12, atol=0)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
