@@ -350,6 +350,7 @@ def main():
     for _ in range(max(args.warmup, 1)):
         l2_flush.zero_()
         lnl, status, iters = trpl.engine.solve_loglik(Xd, problem, want_iters=True)
+    exchange(lnl_steps[:1])                      # NCCL communicator set-up and first-collective cost stay outside the timing
     torch.cuda.synchronize(dev)
     n_bad = int((status != 0).sum().item())
     iters_total = float(iters.sum().item())
@@ -398,15 +399,17 @@ def main():
 
     step_e2e()                                   # warm the e2e path (problem staging, pinned buffers)
     p_tables = torch.zeros((args.steps, E, S), dtype=torch.float64, device=dev)
+    p_stage = torch.zeros((args.steps, E, S), dtype=torch.float64).pin_memory()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
         l2_flush.zero_()
         step_e2e()
-        if world > 1:
-            p_tables[k].copy_(torch.from_numpy(P_host))
-    exchange(p_tables)
+        p_stage[k].numpy()[...] = P_host         # the host-side tables of all steps, exchanged once at the end
+    if world > 1:
+        p_tables.copy_(p_stage, non_blocking=True)
+        exchange(p_tables)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
