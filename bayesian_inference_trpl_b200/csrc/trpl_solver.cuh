@@ -22,6 +22,7 @@ struct Comm {
     int phase;        // ping-pong selector of xb
     int rphase;       // ping-pong selector of red
     double *sb;       // W > 1: interface-system planes [9][SB_STRIDE * W] doubles (tridiag_solve)
+    int solver;       // W > 1: warp that solves the next interface system (rotates after every solve)
     // Row r of the 32*W interface rows lives at slot(r): rows are dealt round-robin into W blocks of
     // 32 (+ padding), so that the solver warp, which takes W CONSECUTIVE rows per lane, and the
     // owning lanes, which touch one row each, both access shared memory without bank conflicts.
@@ -159,9 +160,11 @@ __device__ __forceinline__ void pcr_stage(double &Lr, double &Ur, double &Br, co
 // W == 1: register-local partition sweep over the M-1 interior rows of every lane, then parallel cyclic
 // reduction over the 32 interface rows with warp shuffles.
 // W  > 1 (one CTA per simulation): the same lane-local sweep; the 32*W interface rows are then handed to
-// warp 0 through shared memory, which holds W of them per lane and solves them with the W == 1 code
+// ONE warp through shared memory, which holds W of them per lane and solves them with the W == 1 code
 // (a second partition level + shuffle PCR): two block barriers per solve instead of one per PCR stage
-// over 32*W unknowns.  The neighbour values the caller needs (previous lane's last node, next lane's
+// over 32*W unknowns.  The solver role rotates over the warps from solve to solve: warp k of every CTA
+// sits on scheduler k, so a fixed solver warp would load one scheduler of the SM with the serial part
+// of all resident CTAs (+46 % time per iteration, measured).  The neighbour values the caller needs (previous lane's last node, next lane's
 // first node) are rebuilt from the interface solution, so no further exchange follows the solve.
 // xr receives the new value of the NEXT lane's first node.
 // LAT = latency-optimised variant (multi-warp simulations run 2 warps per scheduler, so dependent
@@ -243,13 +246,14 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
             sb[5 * PL_ + me] = fma(-lr, y[M - 2], b[M - 1]);
             sb[6 * PL_ + me] = u[M - 1];
             __syncthreads();
-            if (g < 32) {
+            if ((g >> 5) == cm.solver) {
+                const int sl_ = g & 31;                            // solver lane: rows W*sl_ .. W*sl_+W-1
                 double L2[W], D2[W], U2[W], B2[W], Z[W];
 #pragma unroll
                 for (int k = 0; k < W; k++) {
-                    const int r = W * g + k;                       // slot(r) = k * ST_ + g
-                    const int here = k * ST_ + g;
-                    const int next = (k + 1 < W) ? here + ST_ : ((g < 31) ? g + 1 : here);
+                    const int r = W * sl_ + k;                     // slot(r) = k * ST_ + sl_
+                    const int here = k * ST_ + sl_;
+                    const int next = (k + 1 < W) ? here + ST_ : ((sl_ < 31) ? sl_ + 1 : here);
                     const double ur = (r < G - 1) ? sb[6 * PL_ + here] : 0.0;
                     L2[k] = sb[3 * PL_ + here];
                     D2[k] = fma(-ur, sb[1 * PL_ + next], sb[4 * PL_ + here]);
@@ -257,19 +261,20 @@ __device__ __forceinline__ double tridiag_solve(const double (&l)[M], const doub
                     B2[k] = fma(-ur, sb[0 * PL_ + next], sb[5 * PL_ + here]);
                 }
                 Comm<1> c1;
-                c1.g = g; c1.xb = nullptr; c1.red = nullptr; c1.phase = 0; c1.rphase = 0; c1.sb = nullptr;
+                c1.g = sl_; c1.xb = nullptr; c1.red = nullptr; c1.phase = 0; c1.rphase = 0; c1.sb = nullptr; c1.solver = 0;
                 double znext;                                      // first row of the next lane
                 tridiag_solve<W, 1, (TRPL_CTA_LAT != 0)>(L2, D2, U2, B2, Z, c1, znext);
 #pragma unroll
                 for (int k = 0; k < W; k++) {
-                    const int here = k * ST_ + g;
-                    const int next = (k + 1 < W) ? here + ST_ : ((g < 31) ? g + 1 : here);
+                    const int here = k * ST_ + sl_;
+                    const int next = (k + 1 < W) ? here + ST_ : ((sl_ < 31) ? sl_ + 1 : here);
                     const double zn = (k + 1 < W) ? Z[k + 1] : znext;
                     sb[7 * PL_ + here] = Z[k];
                     sb[8 * PL_ + here] = fma(-sb[2 * PL_ + next], zn, fma(-sb[1 * PL_ + next], Z[k], sb[0 * PL_ + next]));
                 }
             }
             __syncthreads();
+            cm.solver = (cm.solver + 1) & (W - 1);     // the role rotates: every scheduler gets its share of the serial part
             const double z = sb[7 * PL_ + me];
             const double zl = (g > 0) ? sb[7 * PL_ + Comm<W>::slot(g - 1)] : 0.0;
             xr = (g < G - 1) ? sb[8 * PL_ + me] : 0.0;
@@ -955,7 +960,7 @@ trpl_sim_kernel(const __grid_constant__ KArgs a)
     if (TRPL_DEBUG && lane == 0) reinterpret_cast<unsigned long long *>(ring_warp + 4 * 3 * M * 32)[0] = CANARY_WORD;
     const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
     Comm<1> cm;
-    cm.g = lane; cm.xb = nullptr; cm.red = nullptr; cm.phase = 0; cm.rphase = 0; cm.sb = nullptr;
+    cm.g = lane; cm.xb = nullptr; cm.red = nullptr; cm.phase = 0; cm.rphase = 0; cm.sb = nullptr; cm.solver = 0;
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(a.counter, 1ULL);
@@ -986,7 +991,7 @@ trpl_sim_cta_kernel(const __grid_constant__ KArgs a)
     cm.xb = smem + (size_t)W * (4 * 3 * M * 32 + RING_CANARY);
     cm.red = cm.xb + 2 * Comm<W>::XB_K * 32 * W;
     cm.sb = cm.red + 2 * W * 4;
-    cm.phase = 0; cm.rphase = 0;
+    cm.phase = 0; cm.rphase = 0; cm.solver = blockIdx.x & (W - 1);
     const unsigned long long total = (unsigned long long)a.S * (unsigned long long)a.C;
     for (;;) {
         __syncthreads();
