@@ -463,8 +463,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["desc"] + "; batch of %d samples/GPU/step out of the nominal configuration" % S,
-                       "config": args.config, "samples_per_gpu_per_step": S, "curves": C, "observation_files": E,
+            "config": {"workload": cfg["desc"], "config": args.config,
+                       "batch": "%d samples/GPU/step out of the nominal configuration" % S,
+                       "samples_per_gpu_per_step": S, "curves": C, "observation_files": E,
                        "time_steps_per_sample": steps_per_sample, "sims_resident_per_gpu": resident,
                        "l2": "256 MiB L2 flush between steps", "nonconverged_samples": n_bad,
                        "exchange": "one lnL all-gather + global log-sum-exp after the last step (inside the timed region)",
