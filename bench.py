@@ -13,9 +13,9 @@ Configurations (BASELINE.json `configs`); `power_scan` is the he
   twothick    configs[3]: 6 curves, Length=[311,2000]x3, synthetic observations
   finegrid    configs[4]: L=1000, T=20000 (500 ns), 3 curves, synthetic observations (CTA-per-simulation kernel)
 
-One "step" = one fused launch over S samples per GPU (default S = 2x the simulations resident on the
-GPU / curves * curves, i.e. whole waves); the nominal 1M/4M/16M-sample configurations are this step
-repeated.  Under torchrun every rank owns its own S samples (weak scaling, no data-path collective);
+One "step" = one fused launch over S samples per GPU (default: 12 waves of resident simulations for the
+128-node configurations, 2 waves of resident CTAs on the fine grid); the nominal 1M/4M/16M-sample
+configurations are this step repeated.  Under torchrun every rank owns its own S samples (weak scaling, no data-path collective);
 the only exchange -- all-gather of lnL + global log-sum-exp over NCCL -- happens ONCE, after the last
 step, inside the timed region.  `strong` (N>1 or --strong) times one more step with a fixed global batch
 of 8 x S samples split over the ranks.
@@ -320,7 +320,10 @@ def main():
     cfg = config_def(args.config)
     L, T, C = cfg["L"], cfg["T"], len(cfg["inis"])
     resident = trpl.engine.resident_sims(L, local)
-    S = args.samples if args.samples > 0 else max(1, 2 * resident * 3 // C) if L <= 256 else max(1, 2 * resident // C)
+    # default batch: 12 waves of resident simulations for the 128-node kernel (the tail of a launch, where
+    # warps run out of work items, costs ~0.4 wave: 5 % at 6 waves, 2.5 % at 12, profiles/r02_variants.txt),
+    # 2 waves of resident CTAs on fine grids
+    S = args.samples if args.samples > 0 else max(1, 4 * resident * 3 // C) if L <= 256 else max(1, 2 * resident // C)
     X = prior_samples(S, seed=1234 + rank, stiff=cfg["stiff_prior"])
     e_data = observations(cfg, trpl)
     E = len(e_data)
@@ -398,12 +401,13 @@ def main():
         return P_host
 
     step_e2e()                                   # warm the e2e path (problem staging, pinned buffers)
-    p_tables = torch.zeros((args.steps, E, S), dtype=torch.float64, device=dev)
-    p_stage = torch.zeros((args.steps, E, S), dtype=torch.float64).pin_memory()
+    e2e_steps = min(args.steps, 5)               # same per-step work as above; a handful of steps is enough
+    p_tables = torch.zeros((e2e_steps, E, S), dtype=torch.float64, device=dev)
+    p_stage = torch.zeros((e2e_steps, E, S), dtype=torch.float64).pin_memory()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
+    for k in range(e2e_steps):
         l2_flush.zero_()
         step_e2e()
         p_stage[k].numpy()[...] = P_host         # the host-side tables of all steps, exchanged once at the end
@@ -440,7 +444,7 @@ def main():
 
     if rank == 0:
         value = S * world * args.steps / (ms_total * 1e-3)
-        e2e = S * world * args.steps / (ms_e2e * 1e-3)
+        e2e = S * world * e2e_steps / (ms_e2e * 1e-3)
         tf_peak, _ = trpl.engine.bench_dfma(20000, local)
         achieved = flops_per_step / (kern_mean * 1e-3) / 1e12
         peaks = {}
@@ -472,7 +476,7 @@ def main():
                        "mean_newton_iters_per_step": iters_total / (S * steps_per_sample)},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "h2d_bytes_first_call": h2d_first,
+                    "h2d_bytes_first_call": h2d_first, "steps": e2e_steps,
                     "api": "bayeslib.simulate(model, e_data, P, X, ...) with host numpy arrays; excitations and "
                            "bracketed observations are staged once per (simPar, iniPar, e_data) and reused"},
             "gpu_launches": 2 * args.steps + (3 if world > 1 else 0),   # sim + finish per step (+ 3 lse kernels at the end when sharded)
