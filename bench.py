@@ -14,7 +14,7 @@ Configurations (BASELINE.json `configs`); `power_scan` is the he
   finegrid    configs[4]: L=1000, T=20000 (500 ns), 3 curves, synthetic observations (CTA-per-simulation kernel)
 
 One "step" = one fused launch over S samples per GPU (default: 12 waves of resident simulations for the
-128-node configurations, 2 waves of resident CTAs on the fine grid); the nominal 1M/4M/16M-sample
+128-node configurations, 4 waves of resident CTAs on the fine grid); the nominal 1M/4M/16M-sample
 configurations are this step repeated.  Under torchrun every rank owns its own S samples (weak scaling, no data-path collective);
 the only exchange -- all-gather of lnL + global log-sum-exp over NCCL -- happens ONCE, after the last
 step, inside the timed region.  `strong` (N>1 or --strong) times one more step with a fixed global batch
@@ -322,8 +322,8 @@ def main():
     resident = trpl.engine.resident_sims(L, local)
     # default batch: 12 waves of resident simulations for the 128-node kernel (the tail of a launch, where
     # warps run out of work items, costs ~0.4 wave: 5 % at 6 waves, 2.5 % at 12, profiles/r02_variants.txt),
-    # 2 waves of resident CTAs on fine grids
-    S = args.samples if args.samples > 0 else max(1, 4 * resident * 3 // C) if L <= 256 else max(1, 2 * resident // C)
+    # 4 waves of resident CTAs on fine grids
+    S = args.samples if args.samples > 0 else max(1, 4 * resident * 3 // C) if L <= 256 else max(1, 4 * resident // C)
     X = prior_samples(S, seed=1234 + rank, stiff=cfg["stiff_prior"])
     e_data = observations(cfg, trpl)
     E = len(e_data)

@@ -3,7 +3,7 @@
 parameter samples, 3-curve power scan, L=128, T=80000, on all ranks of a torchrun launch.
 Every rank writes the (synthetic) excitation / observation CSVs in the reference formats, calls
 bayesian_inference_trpl_b200.parallel_bayes_gpu.run(), rank 0 reports throughput and a posterior
-sanity check.   torchrun --nproc-per-node 8 tools/nominal_power_scan.py [log2 num_points]"""
+sanity check.   torchrun --nproc-per-node 8 tools/nominal_power_scan.py [log2 num_points] [numpy|philox]"""
 import json, os, sys, tempfile, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,6 +15,7 @@ from helpers import TRUTH, UC, example_data
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
 n_log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+sampler = sys.argv[2] if len(sys.argv) > 2 else "numpy"        # "philox": every rank draws only its own rows on its GPU
 L, T, Time, Length = 128, 80000, 2000.0, 2000.0
 tmp = tempfile.mkdtemp(prefix="trpl_nominal_r%d_" % rank)
 exc = os.path.join(tmp, "Power_scan_Excitations.csv")
@@ -34,6 +35,9 @@ trpl.bayes_io.write_observations(obs, [grid] * 3, pls)
 cfg = entry.default_config()
 cfg.update(Length=Length, Time=Time, T=T)
 cfg["sim_flags"]["num_points"] = 2 ** n_log2
+cfg["sim_flags"]["sampler"] = sampler
+if sampler == "philox":
+    cfg["minX"][2:4] = 0.5          # mobilities from 0.5 instead of 0 (the numpy path of this tool keeps the entry script's 0)
 out = os.path.join(tmp, "NOMINAL")
 t0 = time.perf_counter()
 P, X = entry.run(exc, [obs], [out], cfg=cfg, posterior=False)
@@ -46,7 +50,7 @@ if rank == 0:
     w = np.exp(lnp - np.nanmax(lnp)); w[~np.isfinite(w)] = 0; w /= w.sum()
     free = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
     names = entry.param_names
-    rep = {"num_points": S, "n_gpus": world, "wall_s": dt, "likelihoods_per_s_incl_io": S / dt,
+    rep = {"num_points": S, "n_gpus": world, "sampler": sampler, "wall_s": dt, "likelihoods_per_s_incl_io": S / dt,
            "nonfinite_lnL": int((~np.isfinite(lnp)).sum()), "best_lnL": float(lnp[best]),
            "effective_sample_size": float(1.0 / np.sum(w ** 2)),
            "best_sample": {names[j]: float(X[best, j]) for j in free},
