@@ -102,6 +102,8 @@ def lib():
     L.trpl_weighted_hist.argtypes = [vp, i64, i64, i32, i32, vp, dbl, dbl, i32, dbl, dbl, i32, vp, i32, vp]
     L.trpl_weighted_moments.restype = i32
     L.trpl_weighted_moments.argtypes = [vp, i64, i64, i32, vp, vp, i32, vp]
+    L.trpl_selftest_rcp.restype = i32
+    L.trpl_selftest_rcp.argtypes = [vp, vp, i64, i32, vp]
     L.trpl_bench_dfma.restype = i32
     L.trpl_bench_dfma.argtypes = [i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     _lib = L
@@ -111,7 +113,7 @@ def lib():
 EXPORTS = ["trpl_version", "trpl_error_string", "trpl_last_cuda_error", "trpl_resident_sims",
            "trpl_solve_pl", "trpl_solve_loglik", "trpl_log10_clamp", "trpl_lnp_accumulate",
            "trpl_obs_prepare", "trpl_lse_partial", "trpl_bench_dfma", "trpl_random_grid",
-           "trpl_posterior_weights", "trpl_weighted_hist", "trpl_weighted_moments"]
+           "trpl_posterior_weights", "trpl_weighted_hist", "trpl_weighted_moments", "trpl_selftest_rcp"]
 
 
 def check(rc, what):

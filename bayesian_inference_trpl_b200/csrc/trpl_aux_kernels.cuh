@@ -338,6 +338,13 @@ trpl_moments_kernel_fixed(const double *x, long long ldx, const double *w, long 
     }
 }
 
+// ---- self-test of the solver's reciprocal (trpl_common.cuh: rcp64) -----------------------------
+__global__ void trpl_rcp_kernel(const double *x, double *y, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) y[i] = rcp64(x[i]);
+}
+
 // ---- FP64 FMA pipe microbenchmark ------------------------------------------------------------
 __global__ void trpl_dfma_kernel(double *out, int iters, double seed)
 {

@@ -529,6 +529,20 @@ int trpl_weighted_moments(const double *d_x, int64_t n, int64_t ldx, int ncol, c
     return TRPL_OK;
 }
 
+int trpl_selftest_rcp(const double *d_x, double *d_y, int64_t n, int device, void *stream)
+{
+    if (!d_x || !d_y || n < 0) return TRPL_EINVAL;
+    DeviceGuard guard;
+    int rc = guard.enter(device);
+    if (rc) return rc;
+    if (n == 0) return TRPL_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    trpl_rcp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n);
+    CK(cudaGetLastError());
+    return TRPL_OK;
+}
+
 int trpl_bench_dfma(int device, int iters, double *tflops, double *ms)
 {
     if (!tflops || iters < 1) return TRPL_EINVAL;

@@ -164,6 +164,13 @@ int trpl_weighted_hist(const double *d_x, int64_t n, int64_t ldx, int colx, int 
 int trpl_weighted_moments(const double *d_x, int64_t n, int64_t ldx, int ncol, const double *d_w,
                           double *d_out, int device, void *stream);
 
+/* Self-test hook: y[i] = the solver's reciprocal of x[i] (MUFU.RCP64H seed + one cubically convergent
+ * step; replaces the reference's FP64 divisions, pvSimPCR.py:57-69,156-209).  Domain = what the solver
+ * feeds it: finite, normal, |x| in [2^-1000, 2^1000]; max error 1 ulp there.  Zero, denormal, infinite or
+ * NaN operands give a non-finite result, which the solver reports as TRPL_ST_NONFINITE for that sample
+ * (the reference would divide by zero at the same place).                                        */
+int trpl_selftest_rcp(const double *d_x, double *d_y, int64_t n, int device, void *stream);
+
 /* FP64 FMA-pipe microbenchmark (roofline denominator): runs `iters` dependent-chain DFMA
  * rounds on every SM and returns the achieved TFLOP/s (2 flop per FMA) in *tflops.
  * Synchronous.                                                                             */

@@ -168,3 +168,28 @@ def test_debug_build_reports_itself(trpl):
     assert v >= 200
     if "debug" in os.path.basename(trpl._lib.LIB_PATH):
         assert v % 2 == 1
+
+
+def test_solver_reciprocal_is_one_ulp_over_its_domain_and_loud_outside(trpl):
+    """rcp64 has no slow path.  Inside the solver's domain (finite, normal, far from the
+    exponent limits) it must be within 1 ulp of 1/x; outside (0, denormal, inf, NaN) the result must be
+    non-finite so that the solver's per-sample non-finite status catches it."""
+    import ctypes
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(1, 2, 200000) * 2.0 ** rng.integers(-1000, 1000, 200000),
+                        -rng.uniform(1, 2, 1000) * 2.0 ** rng.integers(-1000, 1000, 1000),
+                        [1.0, 2.0, 0.5, 3.0, 1e300, 1e-300, np.nextafter(1.0, 2.0), np.nextafter(2.0, 1.0)]])
+    bad = np.array([0.0, -0.0, 5e-324, 1e-310, np.inf, -np.inf, np.nan])
+    xd = torch.from_numpy(np.concatenate([x, bad])).cuda()
+    yd = torch.empty_like(xd)
+    rc = trpl._lib.lib().trpl_selftest_rcp(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(yd.data_ptr()),
+                                           xd.numel(), 0, None)
+    assert rc == 0
+    y = yd.cpu().numpy()
+    good, weird = y[:len(x)], y[len(x):]
+    exact = 1.0 / x
+    ulp = np.abs(good - exact) / np.spacing(np.abs(exact))
+    assert ulp.max() <= 1.0, ulp.max()
+    assert (good[-8:-4] == [1.0, 0.5, 2.0, 1.0 / 3.0]).all()
+    assert not np.isfinite(weird[[0, 1, 2, 3, 6]]).all() and not np.isfinite(weird[[0, 1, 2, 3, 6]]).any()
+    assert (weird[4:6] == 0.0).all() or not np.isfinite(weird[4:6]).any()      # 1/inf = 0 is fine too
