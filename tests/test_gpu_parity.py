@@ -384,7 +384,7 @@ def test_likelihood_properties_at_full_size(trpl):
 # fine grids: one CTA of W warps per simulation (BASELINE config 5 shape: L = 1000)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("L,T", [(1000, 250), (512, 300), (1024, 120), (2048, 60), (260, 300),
-                                 (257, 200), (1001, 120), (774, 150)])
+                                 (257, 200), (1001, 120), (774, 150), (264, 200), (1528, 80)])
 def test_fine_grid_cta_kernel_matches_oracle(trpl, oracle, L, T):
     length = 2000.0
     simPar = [length, 0.025 * T, L, T, 1, (0,), 7, 10000]
