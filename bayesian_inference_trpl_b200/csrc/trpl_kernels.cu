@@ -13,10 +13,12 @@
 //     REGISTERS; the four older BDF levels live in a lane-private shared-memory ring (no
 //     barriers anywhere -- the reference round-trips the state through global memory every
 //     step and needs ~50 __syncthreads per Newton iteration);
-//   * each tridiagonal system is solved by a register-local partition sweep (M-1 interior rows
-//     per lane eliminated in place) + a 32-lane parallel cyclic reduction on the interface
-//     unknowns done with warp shuffles (5 normalised stages instead of the reference's
-//     log2(L)-1 shared-memory stages over all L rows);
+//   * each tridiagonal system is solved by a register-local Thomas sweep over the M-1 interior rows
+//     of every lane (spike vectors to the two interface unknowns) + a 32-lane parallel cyclic reduction
+//     on the interface unknowns done with warp shuffles (at most 5 normalised stages, cut short once
+//     the off-diagonals are negligible, instead of the reference's log2(L)-1 shared-memory stages
+//     over all L rows); fine grids (L > 256) run one CTA per simulation and hand the 32*W interface
+//     rows to one warp (two block barriers per solve);
 //   * the stop rule of both species is reduced together with one 2-value butterfly, division-free;
 //   * PL(t) is a warp reduction; 32 consecutive PL values are staged one per lane and then
 //     consumed together: written with one coalesced store (trpl_solve_pl) and/or turned into

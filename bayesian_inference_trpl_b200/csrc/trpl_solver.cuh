@@ -1,6 +1,7 @@
 // trpl_solver.cuh -- the forward-model + fused-likelihood kernels (the hot path):
 // Comm<W> (lane communication policy), tridiag_solve, Ring, run_sim, trpl_sim_kernel<M,PAD>,
-// trpl_sim_cta_kernel<W,M>.  Replaces pvSimPCR.py:14-293 and bayeslib.py:150-196.
+// trpl_sim_cta_kernel<W,M,PADM>.  Replaces pvSimPCR.py:14-293 and bayeslib.py:150-196.
+// Lines tagged [sec:NAME] delimit the sections profiles/sass_budget.py attributes SASS instructions to.
 #pragma once
 #include "trpl_common.cuh"
 
@@ -9,9 +10,10 @@ namespace trpl {
 // ---------------------------------------------------------------------------------------------
 // Communication among the lanes that share one simulation.  W = warps per simulation.
 //   W == 1: warp shuffles / votes only (the production path for L <= 256).
-//   W  > 1: one CTA of W warps per simulation (fine grids, L up to 32*M*W); values travel through a
-//           ping-pong exchange buffer in shared memory, one __syncthreads per exchange.  Every
-//           thread of the CTA executes the same sequence of exchanges.
+//   W  > 1: one CTA of W warps per simulation (fine grids, L up to 32*M*W).  Generic exchanges (a few per
+//           time step) travel through a ping-pong buffer in shared memory, one __syncthreads each; the
+//           tridiagonal solves use their own planes and two barriers per solve (tridiag_solve); the
+//           stop rule rides on those barriers.  Every thread of the CTA executes the same sequence.
 // g = index of this lane among the 32*W lanes of the simulation.
 // ---------------------------------------------------------------------------------------------
 template <int W>
