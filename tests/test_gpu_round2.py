@@ -193,3 +193,39 @@ def test_solver_reciprocal_is_one_ulp_over_its_domain_and_loud_outside(trpl):
     assert (good[-8:-4] == [1.0, 0.5, 2.0, 1.0 / 3.0]).all()
     assert not np.isfinite(weird[[0, 1, 2, 3, 6]]).all() and not np.isfinite(weird[[0, 1, 2, 3, 6]]).any()
     assert (weird[4:6] == 0.0).all() or not np.isfinite(weird[4:6]).any()      # 1/inf = 0 is fine too
+
+
+def test_slurm_array_tasks_export_their_own_columns_and_merge(trpl, oracle, tmp_path, monkeypatch):
+    """The reference's launcher: independent SLURM array tasks (bayeslib.py:231).  Every task exports, foreign
+    columns are NaN (not 0 = best likelihood), and the merged table equals the single-task run."""
+    exc_path, obs_path, inis, simPar = _files(trpl, oracle, tmp_path, T=160)
+    entry = trpl.parallel_bayes_gpu
+
+    def cfg_for(num_gpus):
+        cfg = entry.default_config()
+        cfg.update(Length=2000.0, Time=simPar[1], T=simPar[3])
+        cfg["ic_flags"]["time_cutoff"] = simPar[1]
+        cfg["sim_flags"]["num_points"] = 23
+        cfg["gpu_info"].update(sims_per_gpu=4, num_gpus=num_gpus)
+        cfg["minX"][2:4] = 0.5
+        return cfg
+
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("SLURM_ARRAY_TASK_ID", raising=False)
+    P1, X1 = entry.run(exc_path, [obs_path], [str(tmp_path / "ONE")], cfg=cfg_for(1))
+    out = str(tmp_path / "ARR")
+    monkeypatch.setenv("SLURM_ARRAY_TASK_COUNT", "3")
+    for k in range(3):
+        monkeypatch.setenv("SLURM_ARRAY_TASK_ID", str(k))
+        Pk, Xk = entry.run(exc_path, [obs_path], [out], cfg=cfg_for(3))
+        mine = trpl.bayeslib.owned_columns(23, {"sims_per_gpu": 4, "num_gpus": 3}, k)
+        assert np.isnan(Pk[0][~mine]).all() and np.isfinite(Pk[0][mine]).all()
+        np.testing.assert_array_equal(Xk, X1)
+        assert os.path.exists(os.path.join("%s_task%d" % (out, k), "ARR_task%d_BAYRAN_P.npy" % k))
+    Pm, Xm = entry.merge_task_exports(out, 3)
+    np.testing.assert_allclose(Pm, P1[0], rtol=1e-12)
+    # a task count that disagrees with the configuration must not silently leave columns uncomputed
+    monkeypatch.setenv("SLURM_ARRAY_TASK_COUNT", "2")
+    monkeypatch.setenv("SLURM_ARRAY_TASK_ID", "0")
+    with pytest.raises(RuntimeError):
+        entry.run(exc_path, [obs_path], [out], cfg=cfg_for(3))
