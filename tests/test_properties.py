@@ -66,3 +66,34 @@ def test_oracle_pcr_and_thomas_agree(seed, L):
     assert (a["status"] == 0).all() and (b["status"] == 0).all()
     np.testing.assert_allclose(a["pl"], b["pl"], rtol=1e-9)
     np.testing.assert_array_equal(a["iters"], b["iters"])
+
+
+@settings(max_examples=40, deadline=None)
+@given(curves=st.lists(st.integers(1, 40), min_size=1, max_size=5), seed=st.integers(0, 2 ** 31 - 1),
+       crlf=st.booleans(), blanks=st.booleans())
+def test_vectorised_observation_reader_equals_row_by_row_parsing(tmp_path_factory, curves, seed, crlf, blanks):
+    """bayes_io.get_data (one vectorised pass) vs a literal row-by-row parse of the reference's format
+    (bayes_io.py:15-60): same curves, same values to the last bit, whatever the line endings."""
+    from bayesian_inference_trpl_b200 import bayes_io
+    rng = np.random.default_rng(seed)
+    nl = "\r\n" if crlf else "\n"
+    lines, expect = [], []
+    for n in curves:
+        t = np.concatenate([[0.0], np.cumsum(rng.uniform(0.01, 1.0, n - 1))]) if n > 1 else np.array([0.0])
+        pl = 10.0 ** rng.uniform(10, 22, n)
+        un = 10.0 ** rng.uniform(8, 15, n)
+        rows = ["%.10G,%.9E,%G" % (a, b, c) for a, b, c in zip(t, pl, un)]
+        expect.append(np.array([[float(x) for x in r.split(",")] for r in rows]))
+        for r in rows:
+            lines.append(r)
+            if blanks and rng.uniform() < 0.1:
+                lines.append("")
+    path = tmp_path_factory.mktemp("obs") / "o.csv"
+    path.write_text(nl.join(lines) + nl + "END" + nl + "1,2,3" + nl, newline="")
+    e = bayes_io.get_data([str(path)], {"time_cutoff": None, "select_obs_sets": None, "noise_level": None},
+                          {"log_pl": False, "self_normalize": False}, scale_f=1.0)[0]
+    assert len(e[0]) == len(curves)
+    for k, ref in enumerate(expect):
+        np.testing.assert_array_equal(e[0][k], ref[:, 0])
+        np.testing.assert_array_equal(e[1][k], ref[:, 1])
+        np.testing.assert_array_equal(e[2][k], ref[:, 2])
