@@ -2,7 +2,6 @@
 computations of the reference GUI back end, `Visualization/utils.py:157-285` (normalize,
 marginalize_1D, marginalize_2D, w_mean, w_variance, covariance), on device tensors, with the
 raw sums all-reduced over the ranks so every rank gets the statistics of ALL samples."""
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -1,7 +1,6 @@
 """Round-2 host-side behaviour on the GPU: the Philox sampler on the product path, the staged-problem
 cache behind bayeslib.simulate, argument guards, the documented command line."""
 import os
-import sys
 
 import numpy as np
 import pytest

@@ -36,7 +36,6 @@ def main():
 
     from baseline import ref_runner as rr
     from helpers import TRUTH, UC, pl_noise_floor, power_scan_excitations, prior_samples
-    import torch
     import bayesian_inference_trpl_b200 as trpl
 
     L = 128
