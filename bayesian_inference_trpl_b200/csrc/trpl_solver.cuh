@@ -7,6 +7,14 @@
 
 namespace trpl {
 
+// BDF1..5 coefficients (a0; a1..a5) of pvSimPCR.py:241-250, one row per order
+__constant__ double c_bdf[5][6] = {
+    {1.0, -1.0, 0.0, 0.0, 0.0, 0.0},
+    {1.5, -2.0, 0.5, 0.0, 0.0, 0.0},
+    {11.0 / 6, -3.0, 1.5, -1.0 / 3, 0.0, 0.0},
+    {25.0 / 12, -4.0, 3.0, -4.0 / 3, 0.25, 0.0},
+    {137.0 / 60, -5.0, 5.0, -10.0 / 3, 1.25, -0.2}};
+
 // ---------------------------------------------------------------------------------------------
 // Communication among the lanes that share one simulation.  W = warps per simulation.
 //   W == 1: warp shuffles / votes only (the production path for L <= 256).
@@ -540,6 +548,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     int t_next_pl = 0;
 
     // consume a block of `cnt` staged PL samples starting at index idx0
+    // [sec:step-flush]
     auto flush = [&](const int idx0, const int cnt) {
         double val;
         if (emu32) {
@@ -617,10 +626,11 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
     // =========================================================================================
     // time loop (pvSimPCR.py:237-293): t = 0 .. t_last, PL(t) emitted from the state at time t
     // =========================================================================================
+    // [sec:step]
     bool failed = false;
     int t;
     for (t = 0; t <= t_last; t++) {
-        // ---- PL(t) = rate * (sum_n N*P - L*N0*P0)                          (pvSimPCR.py:276-281)
+        // [sec:step-PL] ---- PL(t) = rate * (sum_n N*P - L*N0*P0)             (pvSimPCR.py:276-281)
         bool emitted = false;
         if (t == t_next_pl) {
             emitted = true;
@@ -635,24 +645,17 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
             pl_idx++;
         }
 
-        // ---- BDF coefficients, order ramp 1..5                            (pvSimPCR.py:241-250)
-        // (re-selected every step on purpose: as step-local values they stay in uniform registers;
-        // hoisted out of the loop they become loop-carried vector registers and 29 more DFMAs per
-        // iteration turn into the 3-cycle three-register kind)
-        double a0, a1, a2, a3, a4, a5;
-        {
-            int order = t + 1;
-            if (order > 5) order = 5;
-            if (order > a.max_order) order = a.max_order;
-            a2 = a3 = a4 = a5 = 0.0;
-            if (order == 1) { a0 = 1.0; a1 = -1.0; }
-            else if (order == 2) { a0 = 1.5; a1 = -2.0; a2 = 0.5; }
-            else if (order == 3) { a0 = 11.0 / 6; a1 = -3.0; a2 = 1.5; a3 = -1.0 / 3; }
-            else if (order == 4) { a0 = 25.0 / 12; a1 = -4.0; a2 = 3.0; a3 = -4.0 / 3; a4 = 0.25; }
-            else { a0 = 137.0 / 60; a1 = -5.0; a2 = 5.0; a3 = -10.0 / 3; a4 = 1.25; a5 = -0.2; }
-        }
-
-        // ---- history sums bU = a1 U(t) + a2 U(t-1) + ... + a5 U(t-4)       (pvSimPCR.py:133-135)
+        // [sec:step-bdf] ---- BDF coefficients, order ramp 1..5              (pvSimPCR.py:241-250)
+        // (looked up every step on purpose: as step-local values read from the constant bank with a uniform
+        // index they stay in uniform registers; hoisted out of the loop they become loop-carried vector
+        // registers and 29 more DFMAs per iteration turn into the 3-cycle three-register kind.  A table
+        // lookup costs 6 uniform loads; the five-way select it replaces cost 57 moves per step.)
+        int order = t + 1;
+        if (order > 5) order = 5;
+        if (order > a.max_order) order = a.max_order;
+        const double a0 = c_bdf[order - 1][0], a1 = c_bdf[order - 1][1], a2 = c_bdf[order - 1][2];
+        const double a3 = c_bdf[order - 1][3], a4 = c_bdf[order - 1][4], a5 = c_bdf[order - 1][5];
+        // [sec:step-history] ---- history sums bU = a1 U(t) + ... + a5 U(t-4) (pvSimPCR.py:133-135)
         double bN[M], bP[M], bE[M];
 #pragma unroll
         for (int j = 0; j < M; j++) {
@@ -923,7 +926,7 @@ __device__ __forceinline__ void run_sim(const KArgs &a, const int c, const long 
         if (io_warp && emitted && (pl_idx & 31) == 0) flush(pl_idx - 32, 32);
     }
 
-    // ---- tail: partially filled block; after a failure everything from pl_idx on is NaN
+    // [sec:tail] ---- partially filled block; after a failure everything from pl_idx on is NaN
     if (io_warp && (pl_idx & 31)) flush(pl_idx & ~31, pl_idx & 31);
     if (io_warp && failed && cv.pl_out != nullptr) {
         const double qnan = __longlong_as_double(0x7ff8000000000000LL);

@@ -20,6 +20,7 @@ import sys
 
 path, pat = sys.argv[1], sys.argv[2]
 dump = sys.argv[sys.argv.index("--dump") + 1] if "--dump" in sys.argv else None
+outer = "--outer" in sys.argv      # budget of the enclosing TIME loop minus the Newton loop (per-step code)
 src_path = None
 
 # ---- section map from the source: a line `// [sec:NAME]` opens NAME until the next marker
@@ -96,6 +97,10 @@ def _fp64_frac(c):
     return sum(1 for s_ in body_ if op(s_) in ("DFMA", "DMUL", "DADD")) / float(len(body_))
 lo, hi = sorted(cands, key=_fp64_frac)[-1]          # the Newton loop is the FP64-densest big loop
 body = [(a, s, c) for a, s, c in ins if lo <= a <= hi]
+if outer:
+    enclosing = sorted([(l2, h2) for l2, h2 in loops if l2 < lo and h2 > hi], key=lambda c: c[1] - c[0])
+    olo, ohi = enclosing[0]
+    body = [(a, s, c) for a, s, c in ins if olo <= a <= ohi and not (lo <= a <= hi)]
 
 
 def section(chain):
@@ -138,7 +143,8 @@ for a, s, c in body:
         r["other"] += 1
         r["_" + o] += 1
 
-print("kernel %s   Newton loop 0x%x-0x%x   %d instructions" % (pat, lo, hi, len(body)))
+print("kernel %s   %s 0x%x-0x%x   %d instructions" % (pat, "time loop outside the Newton loop (static; the flush block runs once per 32 steps)"
+                                                  if outer else "Newton loop", lo, hi, len(body)))
 print("%-22s" % "section" + "".join("%9s" % k for k in kinds) + "%9s%9s" % ("FP64", "cycles*"))
 tot = collections.Counter()
 for sec, r in rows.items():
